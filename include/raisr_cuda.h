@@ -1,0 +1,86 @@
+/*
+ * raisr_cuda.h -- the thin C ABI of the B200 RAISR engine (plain pointers and sizes, no C++/torch types).
+ *
+ * This is what a foreign-function binding of the reference's hot path would bind: RNLHandler_* in
+ * raisr/RaisrHandler.h forwards to it, and callers that already hold frames in GPU memory (NVDEC/NVENC
+ * pipelines, the bench) use the *_device entry points directly.  Each function cites the reference
+ * code it replaces (paths relative to /root/reference/Library).
+ *
+ * All functions return 0 (RNLErrorNone) or an RNLERRORTYPE value; human-readable diagnostics go to
+ * stdout as "[RAISR ERROR] ..." like the reference's.  There is no CPU fallback: without a CUDA device
+ * raisr_cuda_create fails.
+ */
+#ifndef RAISR_CUDA_H
+#define RAISR_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct raisr_cuda_engine raisr_cuda_engine;
+
+/* numerics of the bucket hash's three square roots and three divisions */
+enum {
+    RAISR_NUMERICS_IEEE = 0,   /* sqrt.rn / div.rn: the specification in oracle/raisr_oracle.c (ORACLE_SQRT_IEEE)          */
+    RAISR_NUMERICS_X86  = 1,   /* reproduces the compiled reference: vrcp14ps(vrsqrt14ps(x)) etc. via lookup tables          */
+    RAISR_NUMERICS_X86_IF_AVAILABLE = 2  /* X86 when the tables are linked in, else IEEE (what RNLHandler_Init asks for)     */
+};
+
+typedef struct raisr_cuda_config {
+    const char *model_path;    /* filter folder: filterbin_2_<bits>[_2], Qfactor_{str,coh}bin_2_<bits>[_2], config            */
+    float ratio;               /* 2.0 or 1.5                                                                                  */
+    unsigned bit_depth;        /* 8, 10 or 16                                                                                 */
+    int range_type;            /* 1 = video range, 2 = full range (RangeType)                                                 */
+    unsigned passes;           /* 1 or 2                                                                                      */
+    unsigned two_pass_mode;    /* 1: upscale in pass 1; 2: upscale in pass 2                                                  */
+    int device;                /* CUDA device ordinal, -1 = current device                                                    */
+    int numerics;              /* RAISR_NUMERICS_*                                                                            */
+    int keep_hash;             /* != 0: keep the per-pass bucket planes for raisr_cuda_read_hash (parity tests)               */
+} raisr_cuda_config;
+
+/* Model loading + engine construction.  Replaces RNLInit (Raisr.cpp:1409-1679) and ReadTrainedData
+ * (Raisr.cpp:246-433): same files, same validation, same messages. */
+int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out);
+
+/* Frame geometry.  Replaces RNLSetRes (Raisr.cpp:1681-1829): no row bands, one device plane per image. */
+int raisr_cuda_set_res(raisr_cuda_engine *e, unsigned in_w, unsigned in_h, unsigned out_w, unsigned out_h,
+                       unsigned in_cw, unsigned in_ch, unsigned out_cw, unsigned out_ch);
+
+/* One frame with HOST planes (steps in bytes), blocking.  Replaces RNLProcess (Raisr.cpp:1294-1397) ->
+ * processSegment (Raisr.cpp:890-1289) + the two chroma resizes (Raisr.cpp:1373-1388).  in_u/in_v/out_u/out_v
+ * may all be NULL for luma-only use. */
+int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
+                            size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
+                            void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending);
+
+/* One frame with DEVICE planes, asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream).
+ * Same computation as above without the copies. */
+int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
+                              size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
+                              void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending,
+                              void *stream);
+
+/* Row-band form of the luma path for multi-GPU sharding (the reference's per-thread bands, Raisr.cpp:1738-1779):
+ * computes output rows [row0, row1) only; in_y still points at row 0 of the full input plane, of which only
+ * the rows the band depends on are read (single-pass configurations). */
+int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, void *out_y,
+                                   size_t out_y_step, int blending, unsigned row0, unsigned row1, void *stream);
+
+/* Bucket plane (int32, -1 where a pixel is not hashed) of pass 0 or 1 of the last frame -> host memory,
+ * w*h entries with w,h the plane that pass ran on.  Needs cfg.keep_hash. */
+int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count);
+
+/* number of kernels the engine launched since creation (bench's gpu_launches) */
+unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e);
+
+/* Replaces RNLDeinit (Raisr.cpp:1842-1909). */
+void raisr_cuda_destroy(raisr_cuda_engine *e);
+
+const char *raisr_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,318 @@
+/*
+ * raisr_oracle.c -- CPU restatement of the reference's per-frame RAISR hot path (fp32 AVX512 flavour).
+ *
+ * TEST INFRASTRUCTURE ONLY (see raisr_oracle.h).  Plain C, IEEE arithmetic, no contraction
+ * (built with -ffp-contract=off -fno-fast-math): every rounding below is one the reference performs.
+ *
+ * All file:line citations are relative to /root/reference/Library.
+ */
+#include "raisr_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- constants (Raisr_globals.h:29, :208-264) ---------------------------------------------- */
+static const float kPI = 3.141592653f;                      /* Raisr_globals.h:29 */
+
+/* The 21 distinct literals of gGaussian2DOriginal (Raisr_globals.h:213-224); the 11x11 table is
+ * symmetric in both axes and under transposition, so G[i][j] = kG[min(i',j')][max(i',j')] with
+ * i' = min(i,10-i).  These are data and are used verbatim (never regenerated from exp()). */
+static const double kG[6][6] = {
+    {7.76554e-05, 0.000239195, 0.0005738, 0.001072, 0.00155975, 0.00176743},
+    {0, 0.000736774, 0.00176743, 0.00330199, 0.00480437, 0.00544406},
+    {0, 0, 0.00423984, 0.00792107, 0.0115251, 0.0130596},
+    {0, 0, 0, 0.0147985, 0.0215317, 0.0243986},
+    {0, 0, 0, 0, 0.0313284, 0.0354998},
+    {0, 0, 0, 0, 0, 0.0402265}};
+
+/* gGaussian2D{8,10,16}bit[i][lane]: lane 0 and lanes 12..15 are zero, lanes 1..11 carry
+ * (float)(NF * literal) with NF a float expression (Raisr_globals.h:204-206). */
+static void gaussian_table(int bits, float w[11][16])
+{
+    float M = bits == 8 ? 255.0f : bits == 10 ? 1023.0f : 65535.0f;
+    float NF = 1.0f / (M * M * 2.0f * 2.0f);
+    for (int i = 0; i < 11; i++) {
+        int ii = i < 5 ? i : 10 - i;
+        for (int l = 0; l < 16; l++) w[i][l] = 0.0f;
+        for (int j = 0; j < 11; j++) {
+            int jj = j < 5 ? j : 10 - j;
+            int a = ii < jj ? ii : jj, b = ii < jj ? jj : ii;
+            w[i][j + 1] = (float)((double)NF * kG[a][b]);
+        }
+    }
+}
+
+void oracle_gaussian_weights(int bits, float *w121)
+{
+    float w[11][16];
+    gaussian_table(bits, w);
+    for (int i = 0; i < 11; i++)
+        for (int j = 0; j < 11; j++) w121[i * 11 + j] = w[i][j + 1];
+}
+
+/* ---- 16-lane horizontal sum, sumitup_ps_512 (Raisr_AVX512.cpp:37-44) ------------------------- */
+static float sum16(const float *a)
+{
+    float t8[8], t4[4], t2[2];
+    for (int j = 0; j < 8; j++) t8[j] = a[j] + a[j + 8];
+    for (int j = 0; j < 4; j++) t4[j] = t8[j] + t8[j + 4];
+    for (int j = 0; j < 2; j++) t2[j] = t4[j] + t4[j + 2];
+    return t2[0] + t2[1];
+}
+
+/* ---- structure tensor of the pixel pair (r,cA),(r,cA+1): computeGTWG_Segment_AVX512_32f
+ *      (Raisr_AVX512.cpp:69-131).  F = fp32 plane, stride W.  g[0..2] = pixel A, g[3..5] = pixel B. */
+static void gtwg_pair(const float *F, int W, int r, int cA, const float wt[11][16], float g[6])
+{
+    float a0A[16] = {0}, a1A[16] = {0}, a2A[16] = {0};
+    float a0B[16] = {0}, a1B[16] = {0}, a2B[16] = {0};
+    const float *base = F + (size_t)(r - 6) * W + (cA - 6);
+    for (int i = 0; i < 11; i++) {
+        const float *ra = base + (size_t)i * W;         /* row r-6+i  */
+        const float *rb = ra + W;                       /* row r-5+i  (the patch row) */
+        const float *rc = rb + W;                       /* row r-4+i  */
+        float gx[16], gy[16];
+        for (int j = 0; j < 16; j++) {
+            gx[j] = rc[j] - ra[j];                                  /* GetGx: :54-57  */
+            gy[j] = rb[(j + 1) & 15] - rb[(j + 15) & 15];           /* GetGy: :59-62 (lane rotates) */
+        }
+        for (int j = 0; j < 16; j++) {
+            float wA = wt[i][j];
+            float wB = wt[i][(j + 15) & 15];                        /* shiftR of the weight row, :111 */
+            a0A[j] = fmaf(gx[j] * wA, gx[j], a0A[j]);               /* GetGTWG: fmadd(mul(a,w),b,acc) :64-67 */
+            a1A[j] = fmaf(gx[j] * wA, gy[j], a1A[j]);
+            a2A[j] = fmaf(gy[j] * wA, gy[j], a2A[j]);
+            a0B[j] = fmaf(gx[j] * wB, gx[j], a0B[j]);
+            a1B[j] = fmaf(gx[j] * wB, gy[j], a1B[j]);
+            a2B[j] = fmaf(gy[j] * wB, gy[j], a2B[j]);
+        }
+    }
+    g[0] = sum16(a0A); g[1] = sum16(a1A); g[2] = sum16(a2A);
+    g[3] = sum16(a0B); g[4] = sum16(a1B); g[5] = sum16(a2B);
+}
+
+/* ---- hash (Raisr_AVX512.cpp:151-258 for 16-wide blocks, Raisr_AVX256.cpp:366-472 for 8-wide) - */
+typedef float (*sqrt_fn)(float);
+static float sqrt_ieee(float x) { return sqrtf(x); }
+static float sqrt_x86_14(float x) { return oracle_x86_rcp14(oracle_x86_rsqrt14(x)); }   /* Raisr_AVX512.cpp:200,221-222 */
+static float sqrt_x86_ps(float x) { return oracle_x86_rcpps(oracle_x86_rsqrtps(x)); }   /* Raisr_AVX256.cpp:419,441-442 */
+
+static float atan2_approx(float y, float x)     /* Raisr_AVX512.cpp:151-173 == Raisr_AVX256.cpp:366-391 */
+{
+    const float ONEQTR_PI = (float)(M_PI / 4.0);
+    const float THRQTR_PI = (float)(3.0 * M_PI / 4.0);
+    float ay = fabsf(y) + 1e-10f;
+    int neg = x < 0.0f;
+    float q = neg ? (x + ay) / (ay - x) : (x - ay) / (x + ay);
+    float base = neg ? THRQTR_PI : ONEQTR_PI;
+    float v = fmaf(fmaf(0.1963f * q, q, -0.9817f), q, base);
+    return (y < 0.0f) ? -1.0f * v : v;
+}
+
+/* wide16 != 0: GetHashValue_AVX512_32f_16Elements; == 0: GetHashValue_AVX256_32f_8Elements, which the
+ * AVX512 build runs on the 8-wide tail blocks of every row (Raisr.cpp:1133-1134, 1247-1250). */
+static int hash_bucket(const float g[3], const oracle_pass_params *p, int wide16)
+{
+    sqrt_fn SQ = p->sqrt_mode == ORACLE_SQRT_X86 ? (wide16 ? sqrt_x86_14 : sqrt_x86_ps) : sqrt_ieee;
+    const float a = g[0], b = g[1], d = g[2];
+    float T = a + d;
+    float ad = a * d, bb = b * b;
+    float D = ad - bb;
+    float s = SQ((T * T) / 4.0f - D);
+    float hT = T / 2.0f;
+    float L1 = hT + s, L2 = hT - s;
+    float x = (b != 0.0f) ? (L1 - d) : 1.0f;
+    float ang = atan2_approx(b, x);
+    ang = ang + ((ang < 0.0f) ? kPI : 0.0f);
+    float s1 = SQ(L1), s2 = SQ(L2);
+    float coh = (s1 - s2) / ((s1 + s2) + 0.00000000000000001f);
+    float str = L1;
+
+    const float qangle = 24.0f / kPI;                   /* gQAngle = gQuantizationAngle / PI, Raisr.cpp:1553 */
+    float fa = floorf(ang * qangle);
+    int ai;
+    if (!(fa >= -2147483648.0f && fa < 2147483648.0f)) ai = (int)0x80000000; /* cvtps_epi32 of NaN/overflow */
+    else ai = (int)fa;
+    if (ai < 0) ai = 0;
+    if (ai > 23) ai = 23;
+    int si, ci;
+    if (wide16) {   /* thresholds <= value; NaN compares false -> 0  (Raisr_AVX512.cpp:242-249) */
+        si = (p->qstr[0] <= str) + (p->qstr[1] <= str);
+        ci = (p->qcoh[0] <= coh) + (p->qcoh[1] <= coh);
+    } else {        /* 2 - [value <= Q0] - [value <= Q1]; NaN -> 2     (Raisr_AVX256.cpp:457-464) */
+        si = 2 - ((str <= p->qstr[0]) + (str <= p->qstr[1]));
+        ci = 2 - ((coh <= p->qcoh[0]) + (coh <= p->qcoh[1]));
+    }
+    return ai * 9 + si * 3 + ci;
+}
+
+/* ---- 121-tap filter, DotProdPatch_AVX512_32f (Raisr_AVX512.cpp:134-149) ---------------------- */
+static float dot_patch(const float *F, int W, int r, int c, const float *f121)
+{
+    float acc[16];
+    float pt[128], ft[128];
+    for (int k = 0; k < 128; k++) {
+        if (k < 121) {
+            pt[k] = F[(size_t)(r - 5 + k / 11) * W + (c - 5 + k % 11)];
+            ft[k] = f121[k];
+        } else { pt[k] = 0.0f; ft[k] = 0.0f; }           /* rows are zero-padded to 128 (Raisr.cpp:299,329-331) */
+    }
+    for (int j = 0; j < 16; j++) acc[j] = pt[j] * ft[j];
+    for (int m = 1; m < 8; m++)
+        for (int j = 0; j < 16; j++) acc[j] = fmaf(pt[16 * m + j], ft[16 * m + j], acc[j]);
+    return sum16(acc);
+}
+
+void oracle_hashed_cols(int W, int *c_end, int *tail_start)
+{
+    /* simulation of the column loop, Raisr.cpp:1065-1066 and 1246-1250, unrollSizePatchBased = 16 */
+    int loopItr = 16, c = 6, tail = -1;
+    while (c + loopItr <= W - 6) {
+        if (loopItr == 8 && tail < 0) tail = c;
+        if (loopItr > 8 && c + 2 * 16 > W - 6) loopItr = 8;
+        c += loopItr;
+    }
+    if (tail < 0) tail = c;
+    if (c_end) *c_end = c;
+    if (tail_start) *tail_start = tail;
+}
+
+/* ---- census blend, CTCountOfBitsChangedSegment_AVX256_32f (Raisr_AVX256.cpp:68-166) ----------- */
+static uint16_t blend_pixel(const float *L, const float *Hh, int W, int r, int c, int lo, int hi)
+{
+    const float lc = L[(size_t)r * W + c], hc = Hh[(size_t)r * W + c];
+    int ham = 0;
+    for (int i = -1; i <= 1; i++)
+        for (int j = -1; j <= 1; j++) {
+            if (i == 0 && j == 0) continue;
+            int a = L[(size_t)(r + i) * W + c + j] < lc;
+            int b = Hh[(size_t)(r + i) * W + c + j] < hc;
+            ham += (a != b);
+        }
+    float w = (float)ham / 8.0f;
+    float w2 = 1.0f - w;
+    /* w*lc is exact (k/8 times an integer < 2^16), so mul+mul+add and any FMA contraction of it agree
+     * unless (1-w)*hc is contracted; tests/test_oracle_vs_ref.py pins which one the compiled reference does. */
+    float v = (w * lc + w2 * hc) + 0.5f;
+    float fv = floorf(v);
+    int iv = (int)fv;
+    if (iv > hi) iv = hi;
+    if (iv < lo) iv = lo;
+    return (uint16_t)iv;
+}
+
+int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
+                int32_t *hash, float *gtwg, float *hr, uint16_t *out)
+{
+    if (!S || !out || !p || !p->filters || W < 1 || H < 1) return -1;
+    if (p->blending != 2) return -1;    /* Randomness blending (Raisr.cpp:1203-1242) is not restated yet */
+    if (p->nptypes != 1 && p->nptypes != 4) return -1;
+    const size_t N = (size_t)W * H;
+    float *L = (float *)malloc(N * sizeof(float));
+    float *Hh = (float *)malloc(N * sizeof(float));
+    if (!L || !Hh) { free(L); free(Hh); return -1; }
+    for (size_t i = 0; i < N; i++) { L[i] = (float)S[i]; Hh[i] = L[i]; }  /* convert + raisr32f := upscaled32f, Raisr.cpp:985-990,1029-1036 */
+    if (hash) for (size_t i = 0; i < N; i++) hash[i] = -1;
+    if (gtwg) memset(gtwg, 0, N * 3 * sizeof(float));
+
+    float wt[11][16];
+    gaussian_table(p->bits, wt);
+    const float flo = (float)p->lo, fhi = (float)p->hi;
+
+    /* hot double loop, Raisr.cpp:1038-1066.  Blocks of 16, then blocks of 8 near the right edge; the first
+     * 8-block starts 8 columns after the last 16-block, i.e. it REDOES that block's second half with the
+     * 8-wide hash (c += loopItr uses the already reduced loopItr, Raisr.cpp:1247-1250). */
+    for (int r = 6; r < H - 6; r++) {
+        int loopItr = 16, c = 6;
+        while (c + loopItr <= W - 6) {
+            for (int pix = 0; pix < loopItr / 2; pix++) {
+                float g[6];
+                int cA = c + 2 * pix;
+                gtwg_pair(L, W, r, cA, wt, g);
+                for (int q = 0; q < 2; q++) {
+                    int cc = cA + q;
+                    int hv = hash_bucket(g + 3 * q, p, loopItr == 16);
+                    int pt = p->nptypes == 4 ? (((r - 5) % 2) * 2 + ((cc - 5) % 2)) : 0;     /* Raisr.cpp:1068-1096 */
+                    const float *f = p->filters + ((size_t)hv * p->nptypes + pt) * 121;
+                    float cur = dot_patch(L, W, r, cc, f);
+                    if (cur > flo && cur < fhi) Hh[(size_t)r * W + cc] = cur;                /* Raisr.cpp:1192-1196 */
+                    if (hash) hash[(size_t)r * W + cc] = hv;
+                    if (gtwg) memcpy(gtwg + ((size_t)r * W + cc) * 3, g + 3 * q, 3 * sizeof(float));
+                }
+            }
+            if (loopItr > 8 && c + 2 * 16 > W - 6) loopItr = 8;
+            c += loopItr;
+        }
+    }
+    if (hr) memcpy(hr, Hh, N * sizeof(float));
+
+    /* borders: everything the blend below does not overwrite is the integer upscale itself, unclamped
+     * (row/edge memcpys, Raisr.cpp:999-1028, 1252-1265) */
+    for (size_t i = 0; i < N; i++) out[i] = S[i];
+    for (int r = 1; r < H - 1; r++)
+        for (int c = 1; c < W - 1; c++) out[(size_t)r * W + c] = blend_pixel(L, Hh, W, r, c, p->lo, p->hi);
+    free(L); free(Hh);
+    return 0;
+}
+
+/* ---- cheap upscale: restates oracle/ipp_standin/ipp.h (exact rational bilinear) --------------- */
+static void axis_map(int d, int srcDim, int dstDim, int *i0, int *i1, long long *w1, long long *den)
+{
+    long long D = 2LL * dstDim;
+    long long num = (2LL * d + 1) * srcDim - dstDim;
+    long long q = num >= 0 ? num / D : -((-num + D - 1) / D);
+    long long rr = num - q * D;
+    int a = (int)q, b = (int)q + 1;
+    if (a < 0) a = 0;
+    if (a > srcDim - 1) a = srcDim - 1;
+    if (b < 0) b = 0;
+    if (b > srcDim - 1) b = srcDim - 1;
+    *i0 = a; *i1 = b; *w1 = rr; *den = D;
+}
+
+void oracle_resize(const uint16_t *in, int inW, int inH, uint16_t *out, int outW, int outH)
+{
+    for (int y = 0; y < outH; y++) {
+        int j0, j1; long long wy1, dy;
+        axis_map(y, inH, outH, &j0, &j1, &wy1, &dy);
+        for (int x = 0; x < outW; x++) {
+            int i0, i1; long long wx1, dx;
+            axis_map(x, inW, outW, &i0, &i1, &wx1, &dx);
+            long long wy0 = dy - wy1, wx0 = dx - wx1, DD = dx * dy;
+            long long s = wy0 * (wx0 * in[(size_t)j0 * inW + i0] + wx1 * in[(size_t)j0 * inW + i1]) +
+                          wy1 * (wx0 * in[(size_t)j1 * inW + i0] + wx1 * in[(size_t)j1 * inW + i1]);
+            out[(size_t)y * outW + x] = (uint16_t)((s + DD / 2) / DD);
+        }
+    }
+}
+
+int oracle_process_y(const uint16_t *in, int inW, int inH, uint16_t *out, int outW, int outH,
+                     int passes, int mode, const oracle_pass_params *p1, const oracle_pass_params *p2,
+                     int32_t *hash1, int32_t *hash2)
+{
+    if (passes != 1 && passes != 2) return -1;
+    if (passes == 1) mode = 1;                          /* mode 2 is ignored with one pass, Raisr.cpp:1434-1435 */
+    int rc = -1;
+    uint16_t *up = NULL, *mid = NULL;
+    if (passes == 1 || mode == 1) {
+        up = (uint16_t *)malloc((size_t)outW * outH * sizeof(uint16_t));
+        if (!up) return -1;
+        oracle_resize(in, inW, inH, up, outW, outH);
+        if (passes == 1) { rc = oracle_pass(up, outW, outH, p1, hash1, NULL, NULL, out); goto done; }
+        mid = (uint16_t *)malloc((size_t)outW * outH * sizeof(uint16_t));
+        if (!mid) goto done;
+        rc = oracle_pass(up, outW, outH, p1, hash1, NULL, NULL, mid);          /* quantised intermediate, Raisr.cpp:919-927 */
+        if (rc == 0) rc = oracle_pass(mid, outW, outH, p2, hash2, NULL, NULL, out);
+    } else {
+        mid = (uint16_t *)malloc((size_t)inW * inH * sizeof(uint16_t));
+        up = (uint16_t *)malloc((size_t)outW * outH * sizeof(uint16_t));
+        if (!mid || !up) goto done;
+        rc = oracle_pass(in, inW, inH, p1, hash1, NULL, NULL, mid);            /* pass 1 at input resolution */
+        if (rc != 0) goto done;
+        oracle_resize(mid, inW, inH, up, outW, outH);                           /* pass 2 upscales, Raisr.cpp:945 */
+        rc = oracle_pass(up, outW, outH, p2, hash2, NULL, NULL, out);
+    }
+done:
+    free(up); free(mid);
+    return rc;
+}

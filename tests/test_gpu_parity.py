@@ -1,0 +1,104 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact is the bar (integer output planes and bucket indices)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import raisr_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("raisr_binding", os.path.join(T.PKG_DIR, "binding.py"))
+B = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(B)
+
+
+def run_engine(folder, img, ratio=2.0, bits=8, passes=1, mode=1, rng=T.VideoRange, numerics=B.NUMERICS_IEEE,
+               want_hash=True, out_pad=0):
+    H, W = img.shape
+    oW, oH = int(W * ratio), int(H * ratio)
+    eng = B.Engine(folder, ratio, bits, rng, passes, mode, numerics=numerics, keep_hash=want_hash)
+    eng.set_res(W, H, oW, oH)
+    outb = np.zeros((oH, oW + out_pad), img.dtype)
+    out = outb[:, :oW]
+    rc = eng.process_host(img, out)
+    assert rc == 0
+    hashes = []
+    if want_hash:
+        for i in range(passes):
+            lr = passes == 2 and mode == 2 and i == 0
+            hashes.append(eng.read_hash(i, W if lr else oW, H if lr else oH))
+    n = eng.launch_count()
+    eng.close()
+    assert n >= passes
+    return out.copy(), hashes
+
+
+def oracle_models(folder, bits, passes, rng=T.VideoRange, sqrt_mode=0):
+    m1 = T.OracleModel(folder, bits, False, rng, sqrt_mode)
+    m2 = T.OracleModel(folder, bits, True, rng, sqrt_mode) if passes == 2 else None
+    return m1, m2
+
+
+CASES = [
+    # folder, ratio, bits, passes, mode, (w, h), kind
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (480, 270), "mix"),
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (250, 131), "noise"),      # ragged: width not a multiple of 8/16
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (64, 40), "edges"),
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1, (320, 180), "mix"),
+    ("filters_2x/filters_denoise", 2.0, 8, 2, 2, (320, 180), "mix"),
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (320, 180), "mix"),
+    ("filters_2x/filters_highres", 2.0, 10, 1, 1, (322, 182), "edges"),
+    ("filters_1.5x/filters_highres", 1.5, 8, 1, 1, (320, 180), "mix"),
+    ("filters_1.5x/filters_denoise", 1.5, 8, 2, 2, (426, 240), "noise"),
+]
+
+
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size,kind", CASES)
+def test_bit_exact_vs_oracle(folder, ratio, bits, passes, mode, size, kind):
+    w, h = size
+    f = T.filter_folder(folder)
+    img = T.synth_frame(w, h, bits, seed=1234 + w, kind=kind)
+    out, hashes = run_engine(f, img, ratio, bits, passes, mode)
+    m1, m2 = oracle_models(f, bits, passes)
+    ref, h1, h2 = T.oracle_process_y(img, int(w * ratio), int(h * ratio), m1, m2, passes, mode, want_hash=True)
+    assert np.array_equal(hashes[0], h1), "pass-1 buckets differ: %d" % (hashes[0] != h1).sum()
+    if passes == 2:
+        assert np.array_equal(hashes[1], h2), "pass-2 buckets differ: %d" % (hashes[1] != h2).sum()
+    assert np.array_equal(out, ref), "Y differs on %d px, max %d" % (
+        (out != ref).sum(), np.abs(out.astype(int) - ref.astype(int)).max())
+
+
+def test_full_range_and_padded_step():
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = T.synth_frame(200, 120, 8, seed=5, kind="noise")
+    out, _ = run_engine(f, img, rng=T.FullRange, want_hash=False, out_pad=64)
+    m1, _ = oracle_models(f, 8, 1, rng=T.FullRange)
+    ref = T.oracle_process_y(img, 400, 240, m1)
+    assert np.array_equal(out, ref)
+
+
+def test_handler_api_yuv420():
+    """RNLHandler_* call sequence of vf_raisr.c with chroma planes; chroma = exact-rational bilinear."""
+    f = T.filter_folder("filters_2x/filters_lowres")
+    w, h = 256, 144
+    img = T.synth_frame(w, h, 8, seed=77)
+    u, v = T.synth_chroma(w // 2, h // 2, 8, 1), T.synth_chroma(w // 2, h // 2, 8, 2)
+    os.environ["RAISR_CUDA_NUMERICS"] = "0"
+    L = T.handler_lib(T.product_lib_path())
+    oy, ou, ov = T.run_handler(L, f, img, inU=u, inV=v, frames=2)
+    m1, _ = oracle_models(f, 8, 1)
+    assert np.array_equal(oy, T.oracle_process_y(img, 2 * w, 2 * h, m1))
+    assert np.array_equal(ou, T.oracle_resize(u, w, h))
+    assert np.array_equal(ov, T.oracle_resize(v, w, h))
+
+
+def test_constant_frame_invariants():
+    """constant input v -> unfiltered border = clamp(v), 1-px frame = v."""
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = np.full((60, 80), 7, np.uint8)        # below video-range minimum 16
+    out, _ = run_engine(f, img, want_hash=False)
+    assert (out[0, :] == 7).all() and (out[-1, :] == 7).all() and (out[:, 0] == 7).all() and (out[:, -1] == 7).all()
+    assert (out[1:6, 1:-1] == 16).all()

@@ -1,0 +1,476 @@
+// raisr_engine.cu -- host side of the B200 RAISR engine behind include/raisr_cuda.h.
+//
+// Owns the model tables, the device planes and the launch plan of a frame:
+//   passes=1          : [upscale+filter] in -> out
+//   passes=2, mode=1  : [upscale+filter, set 1] in -> mid(HR)   ; [filter, set 2] mid -> out
+//   passes=2, mode=2  : [filter, set 1] in -> mid(LR)           ; [upscale+filter, set 2] mid -> out
+// (the reference's pass control, Library/Raisr.cpp:896-975), plus one resize launch per chroma plane
+// (Raisr.cpp:1373-1388).  The pass-1 -> pass-2 dependency is stream order; the intermediate plane is
+// quantised to u8/u16 exactly like gIntermediateY (Raisr.cpp:919-927, 1716-1723).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "raisr/RaisrDefaults.h"
+#include "raisr_cuda.h"
+#include "raisr_kernels.cuh"
+#include "raisr_model.h"
+#include "x86_tables.h"
+
+namespace raisr {
+
+#define CUDA_OK(call)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t err__ = (call);                                                                            \
+        if (err__ != cudaSuccess) {                                                                            \
+            std::cout << "[RAISR ERROR] CUDA failure: " << cudaGetErrorString(err__) << " at " << __FILE__ << ":" \
+                      << __LINE__ << std::endl;                                                                \
+            return RNLErrorInsufficientResources;                                                              \
+        }                                                                                                      \
+    } while (0)
+
+// One axis of the cheap upscale: dst index d samples src at ((2d+1)*src - dst) / (2*dst), replicate border,
+// weights kept as exact integers over a common (gcd-reduced) denominator.  Definition: oracle/ipp_standin/ipp.h.
+struct AxisMap {
+    std::vector<int> map, w;   // map[d] = i0 << 1 | (i1 != i0);  w[d] = weight numerator of tap i1
+    int den = 1;
+    int *d_map = nullptr, *d_w = nullptr;
+    void build(int src, int dst)
+    {
+        map.resize(dst);
+        w.resize(dst);
+        const long long D = 2LL * dst;
+        long long g = D;
+        for (int d = 0; d < dst; ++d) {
+            const long long num = (2LL * d + 1) * src - dst;
+            const long long q = num >= 0 ? num / D : -((-num + D - 1) / D);
+            const long long r = num - q * D;
+            long long a = q, b = q + 1;
+            a = std::min<long long>(std::max<long long>(a, 0), src - 1);
+            b = std::min<long long>(std::max<long long>(b, 0), src - 1);
+            map[d] = (int)(a << 1) | (b != a);
+            w[d] = (int)r;
+            g = std::gcd(g, r);
+        }
+        den = (int)(D / g);
+        for (int d = 0; d < dst; ++d) w[d] = (int)(w[d] / g);
+    }
+    int upload()
+    {
+        release();
+        CUDA_OK(cudaMalloc(&d_map, map.size() * sizeof(int)));
+        CUDA_OK(cudaMalloc(&d_w, w.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(d_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_w, w.data(), w.size() * sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release()
+    {
+        cudaFree(d_map);
+        cudaFree(d_w);
+        d_map = d_w = nullptr;
+    }
+};
+
+struct Plane {
+    void *ptr = nullptr;
+    size_t pitch = 0;
+    int w = 0, h = 0;
+    int alloc(int w_, int h_, int bps)
+    {
+        release();
+        w = w_; h = h_;
+        CUDA_OK(cudaMallocPitch(&ptr, &pitch, (size_t)w * bps, h));
+        return 0;
+    }
+    void release() { cudaFree(ptr); ptr = nullptr; }
+};
+
+// hashed column range of a row: the reference's column loop (Raisr.cpp:1065-1066,1246-1250) run symbolically
+static void hashed_cols(int W, int *c_end, int *tail_start, int *ov_end)
+{
+    int step = 16, c = 6, tail = -1, last16 = -1;
+    while (c + step <= W - 6) {
+        if (step == 16) last16 = c; else if (tail < 0) tail = c;
+        if (step > 8 && c + 32 > W - 6) step = 8;
+        c += step;
+    }
+    if (tail < 0) tail = c;
+    *c_end = c;
+    *tail_start = tail;
+    *ov_end = last16 >= 0 ? std::min(last16 + 16, c) : tail;
+}
+
+}  // namespace raisr
+
+using namespace raisr;
+
+struct raisr_cuda_engine {
+    raisr_cuda_config cfg{};
+    std::string model_path;
+    Model model;
+    int bps = 1;                    // bytes per sample
+    int lo = 0, hi = 255;
+    int device = 0;
+    float *d_filters[2] = {nullptr, nullptr};
+    uint16_t *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};
+    // geometry
+    bool have_res = false;
+    int in_w = 0, in_h = 0, out_w = 0, out_h = 0, in_cw = 0, in_ch = 0, out_cw = 0, out_ch = 0;
+    AxisMap yx, yy, cx, cy;
+    Plane d_in[3], d_out[3], d_mid;
+    int *d_hash[2] = {nullptr, nullptr};
+    int hash_w[2] = {0, 0}, hash_h[2] = {0, 0};
+    cudaStream_t stream = nullptr, stream_uv = nullptr;
+    cudaEvent_t ev_uv = nullptr, ev_in = nullptr;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+int fill_weights(unsigned bits)
+{
+    // the 21 distinct literals of gGaussian2DOriginal (Raisr_globals.h:213-224), G[i][j] = kG[min][max] after folding
+    static const double kG[6][6] = {
+        {7.76554e-05, 0.000239195, 0.0005738, 0.001072, 0.00155975, 0.00176743},
+        {0, 0.000736774, 0.00176743, 0.00330199, 0.00480437, 0.00544406},
+        {0, 0, 0.00423984, 0.00792107, 0.0115251, 0.0130596},
+        {0, 0, 0, 0.0147985, 0.0215317, 0.0243986},
+        {0, 0, 0, 0, 0.0313284, 0.0354998},
+        {0, 0, 0, 0, 0, 0.0402265}};
+    const float M = bits == 8 ? 255.0f : bits == 10 ? 1023.0f : 65535.0f;
+    const float NF = 1.0f / (M * M * 2.0f * 2.0f);                       // NF_8 / NF_10 / NF_16, Raisr_globals.h:204-206
+    float w[11][6];
+    for (int i = 0; i < 11; ++i) {
+        const int ii = i < 5 ? i : 10 - i;
+        for (int m = 0; m < 6; ++m) w[i][m] = (float)((double)NF * kG[std::min(ii, m)][std::max(ii, m)]);
+    }
+    CUDA_OK(cudaMemcpyToSymbol(c_gw, w, sizeof(w)));
+    return 0;
+}
+
+template <typename PixT>
+int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_done = true;
+    }
+    const dim3 grid((p.W + TW - 1) / TW, (p.row1 - p.row0 + TH - 1) / TH);
+    raisr_pass_kernel<PixT><<<grid, NT, SMEM_BYTES, s>>>(p);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+int launch_pass(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
+{
+    return e->bps == 1 ? launch_pass_t<uint8_t>(e, p, s) : launch_pass_t<uint16_t>(e, p, s);
+}
+
+int launch_resize(raisr_cuda_engine *e, const void *in, size_t in_pitch, void *out, size_t out_pitch, cudaStream_t s)
+{
+    ResizeParams rp{in, in_pitch, e->in_cw, e->in_ch, out, out_pitch, e->out_cw, e->out_ch,
+                    e->cx.d_map, e->cx.d_w, e->cy.d_map, e->cy.d_w, e->cx.den, e->cy.den};
+    const dim3 grid((rp.W + 63) / 64, (rp.H + 15) / 16);
+    if (e->bps == 1) resize_kernel<uint8_t><<<grid, 256, 0, s>>>(rp);
+    else resize_kernel<uint16_t><<<grid, 256, 0, s>>>(rp);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+// fills the per-pass constant part of PassParams
+void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
+{
+    const PassModel &pm = e->model.pass[pass_idx];
+    p->filters = e->d_filters[pass_idx];
+    p->ptypes = pm.ptypes;
+    p->qstr0 = pm.qstr[0]; p->qstr1 = pm.qstr[1];
+    p->qcoh0 = pm.qcoh[0]; p->qcoh1 = pm.qcoh[1];
+    p->lo = e->lo; p->hi = e->hi;
+    hashed_cols(W, &p->c_end, &p->tail_start, &p->ov_end);
+    p->numerics = e->cfg.numerics;
+    p->qangle = (float)e->model.q_angle / 3.141592653f;      // gQAngle = gQuantizationAngle / PI (Raisr.cpp:1553)
+    p->nangles = e->model.q_angle;
+    p->hash_out = e->d_hash[pass_idx];
+    p->blending = 2;
+    p->lut_rsqrt14 = e->d_lut[0]; p->lut_rcp14 = e->d_lut[1]; p->lut_rsqrtps = e->d_lut[2]; p->lut_rcpps = e->d_lut[3];
+}
+
+void set_upscale(const raisr_cuda_engine *e, PassParams *p)
+{
+    p->upscale = 1;
+    p->xmap = e->yx.d_map; p->xw = e->yx.d_w; p->ymap = e->yy.d_map; p->yw = e->yy.d_w;
+    p->denx = e->yx.den; p->deny = e->yy.den;
+}
+
+// the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
+int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
+             cudaStream_t s)
+{
+    const bool two = e->cfg.passes == 2;
+    const bool mode2 = two && e->cfg.two_pass_mode == 2;
+    if (!two) {
+        PassParams p{};
+        p.in = in_y; p.in_pitch = in_step; p.in_w = e->in_w; p.in_h = e->in_h;
+        p.out = out_y; p.out_pitch = out_step; p.W = e->out_w; p.H = e->out_h; p.row0 = row0; p.row1 = row1;
+        pass_common(e, 0, p.W, &p);
+        set_upscale(e, &p);
+        return launch_pass(e, p, s);
+    }
+    if (row0 != 0 || row1 != e->out_h) {
+        std::cout << "[RAISR ERROR] row bands are only available with passes=1" << std::endl;
+        return RNLErrorBadParameter;
+    }
+    PassParams p1{}, p2{};
+    p1.in = in_y; p1.in_pitch = in_step; p1.in_w = e->in_w; p1.in_h = e->in_h;
+    p1.out = e->d_mid.ptr; p1.out_pitch = e->d_mid.pitch; p1.W = e->d_mid.w; p1.H = e->d_mid.h; p1.row0 = 0; p1.row1 = p1.H;
+    pass_common(e, 0, p1.W, &p1);
+    if (!mode2) set_upscale(e, &p1);
+    p2.in = e->d_mid.ptr; p2.in_pitch = e->d_mid.pitch; p2.in_w = e->d_mid.w; p2.in_h = e->d_mid.h;
+    p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = 0; p2.row1 = p2.H;
+    pass_common(e, 1, p2.W, &p2);
+    if (mode2) set_upscale(e, &p2);
+    int rc = launch_pass(e, p1, s);
+    if (rc) return rc;
+    return launch_pass(e, p2, s);
+}
+
+int check_blending(int blending)
+{
+    if (blending == CountOfBitsChanged) return 0;
+    std::cout << "[RAISR ERROR] blending mode " << blending << " is not available in the CUDA engine (only CountOfBitsChanged = 2)" << std::endl;
+    return RNLErrorBadParameter;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *raisr_cuda_version(void) { return "raisr-b200 0.1 (API 23.11)"; }
+
+int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
+{
+    if (!cfg || !out || !cfg->model_path) return RNLErrorBadParameter;
+    *out = nullptr;
+    unsigned passes = cfg->passes, mode = cfg->two_pass_mode;
+    // pass control, Raisr.cpp:1429-1439
+    if (passes == 2) {
+        std::cout << "--------------- running 2 pass ---------------\n";
+        if (mode != 1 && mode != 2) {
+            std::cout << "[RAISR ERROR] Only support two pass mode 1 or 2. " << std::endl;
+            return RNLErrorUndefined;
+        }
+    } else if (passes == 1 && mode == 2) {
+        std::cout << "[RAISR WARNING] 1 pass with upscale in 2d pass, mode = 2 ignored !" << std::endl;
+        mode = 1;
+    } else if (passes != 1) {
+        std::cout << "[RAISR ERROR] Only support passes 1 or 2. " << std::endl;
+        return RNLErrorUndefined;
+    } else {
+        mode = 1;
+    }
+    if (cfg->bit_depth != 8 && cfg->bit_depth != 10 && cfg->bit_depth != 16) {     // Raisr.cpp:1446-1474
+        std::cout << "[RAISR ERROR] bit depth: " << cfg->bit_depth << "bits is NOT supported." << std::endl;
+        return RNLErrorBadParameter;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        std::cout << "[RAISR ERROR] no CUDA device: the B200 engine has no CPU path" << std::endl;
+        return RNLErrorUndefined;
+    }
+    raisr_cuda_engine *e = new raisr_cuda_engine;
+    e->cfg = *cfg;
+    e->cfg.passes = passes;
+    e->cfg.two_pass_mode = mode;
+    e->model_path = cfg->model_path;
+    e->cfg.model_path = e->model_path.c_str();
+    e->bps = cfg->bit_depth == 8 ? 1 : 2;
+    const bool video = cfg->range_type == VideoRange;
+    if (cfg->bit_depth == 8) { e->lo = video ? 16 : 0; e->hi = video ? 235 : 255; }
+    else if (cfg->bit_depth == 10) { e->lo = video ? 64 : 0; e->hi = video ? 940 : 1023; }
+    else { e->lo = 0; e->hi = 65535; }
+
+    int rc = load_model(e->model_path, cfg->ratio, cfg->bit_depth, passes, &e->model);
+    if (rc != RNLErrorNone) { delete e; return rc; }
+
+    auto fail = [&](int code) { raisr_cuda_destroy(e); return code; };
+    if (cfg->device >= 0) {
+        if (cudaSetDevice(cfg->device) != cudaSuccess) {
+            std::cout << "[RAISR ERROR] cannot select CUDA device " << cfg->device << std::endl;
+            return fail(RNLErrorBadParameter);
+        }
+    }
+    if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
+    for (unsigned i = 0; i < passes; ++i) {
+        const size_t bytes = e->model.pass[i].filters.size() * sizeof(float);
+        if (cudaMalloc(&e->d_filters[i], bytes) != cudaSuccess ||
+            cudaMemcpy(e->d_filters[i], e->model.pass[i].filters.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(RNLErrorInsufficientResources);
+    }
+    if (e->cfg.numerics == RAISR_NUMERICS_X86_IF_AVAILABLE) {
+        const uint16_t *src[4]; size_t n[4];
+        x86_tables(src, n);
+        e->cfg.numerics = (src[0] && src[1] && src[2] && src[3]) ? RAISR_NUMERICS_X86 : RAISR_NUMERICS_IEEE;
+    }
+    if (e->cfg.numerics == RAISR_NUMERICS_X86) {
+        const uint16_t *src[4]; size_t n[4];
+        x86_tables(src, n);
+        for (int i = 0; i < 4; ++i) {
+            if (!src[i]) {
+                std::cout << "[RAISR ERROR] x86 numerics tables are not built into this library" << std::endl;
+                return fail(RNLErrorBadParameter);
+            }
+            if (cudaMalloc(&e->d_lut[i], n[i] * sizeof(uint16_t)) != cudaSuccess ||
+                cudaMemcpy(e->d_lut[i], src[i], n[i] * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(RNLErrorInsufficientResources);
+        }
+    }
+    if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream_uv, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_uv, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess)
+        return fail(RNLErrorInsufficientResources);
+    *out = e;
+    return RNLErrorNone;
+}
+
+int raisr_cuda_set_res(raisr_cuda_engine *e, unsigned in_w, unsigned in_h, unsigned out_w, unsigned out_h,
+                       unsigned in_cw, unsigned in_ch, unsigned out_cw, unsigned out_ch)
+{
+    if (!e || !in_w || !in_h || !out_w || !out_h) return RNLErrorBadParameter;
+    CUDA_OK(cudaSetDevice(e->device));
+    e->in_w = in_w; e->in_h = in_h; e->out_w = out_w; e->out_h = out_h;
+    e->in_cw = in_cw; e->in_ch = in_ch; e->out_cw = out_cw; e->out_ch = out_ch;
+    // the resize spec of the reference maps {inW, (int)(outH / ratio)} -> {outW, outH} (Raisr.cpp:1801-1803)
+    int src_h = (int)((float)out_h / e->cfg.ratio);
+    if (src_h > (int)in_h) src_h = in_h;
+    if (src_h < 1) src_h = 1;
+    e->yx.build(in_w, out_w);
+    e->yy.build(src_h, out_h);
+    if (e->yx.upload() || e->yy.upload()) return RNLErrorInsufficientResources;
+    if (in_cw && in_ch && out_cw && out_ch) {
+        e->cx.build(in_cw, out_cw);
+        e->cy.build(in_ch, out_ch);
+        if (e->cx.upload() || e->cy.upload()) return RNLErrorInsufficientResources;
+    }
+    if (e->d_in[0].alloc(in_w, in_h, e->bps) || e->d_out[0].alloc(out_w, out_h, e->bps)) return RNLErrorInsufficientResources;
+    if (in_cw && in_ch && out_cw && out_ch)
+        for (int i = 1; i < 3; ++i)
+            if (e->d_in[i].alloc(in_cw, in_ch, e->bps) || e->d_out[i].alloc(out_cw, out_ch, e->bps))
+                return RNLErrorInsufficientResources;
+    if (e->cfg.passes == 2) {
+        const bool mode2 = e->cfg.two_pass_mode == 2;       // intermediate is LR-sized in mode 2 (Raisr.cpp:1703-1723)
+        if (e->d_mid.alloc(mode2 ? in_w : out_w, mode2 ? in_h : out_h, e->bps)) return RNLErrorInsufficientResources;
+    }
+    for (int i = 0; i < 2; ++i) { cudaFree(e->d_hash[i]); e->d_hash[i] = nullptr; }
+    if (e->cfg.keep_hash) {
+        for (unsigned i = 0; i < e->cfg.passes; ++i) {
+            const bool lr = e->cfg.passes == 2 && e->cfg.two_pass_mode == 2 && i == 0;
+            e->hash_w[i] = lr ? in_w : out_w;
+            e->hash_h[i] = lr ? in_h : out_h;
+            CUDA_OK(cudaMalloc(&e->d_hash[i], sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i]));
+        }
+    }
+    e->have_res = true;
+    return RNLErrorNone;
+}
+
+int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, void *out_y,
+                                   size_t out_y_step, int blending, unsigned row0, unsigned row1, void *stream)
+{
+    if (!e || !e->have_res || !in_y || !out_y || row0 >= row1 || row1 > (unsigned)e->out_h) return RNLErrorBadParameter;
+    if (check_blending(blending)) return RNLErrorBadParameter;
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (unsigned i = 0; i < e->cfg.passes; ++i)
+        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
+    return run_luma(e, in_y, in_y_step, out_y, out_y_step, (int)row0, (int)row1, s);
+}
+
+int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
+                              size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
+                              void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending, void *stream)
+{
+    if (!e || !e->have_res) return RNLErrorBadParameter;
+    int rc = raisr_cuda_process_device_rows(e, in_y, in_y_step, out_y, out_y_step, blending, 0, e->out_h, stream);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (in_u && out_u) { rc = launch_resize(e, in_u, in_u_step, out_u, out_u_step, s); if (rc) return rc; }
+    if (in_v && out_v) { rc = launch_resize(e, in_v, in_v_step, out_v, out_v_step, s); if (rc) return rc; }
+    return RNLErrorNone;
+}
+
+int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
+                            size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
+                            void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending)
+{
+    if (!e || !e->have_res || !in_y || !out_y) return RNLErrorBadParameter;
+    if (check_blending(blending)) return RNLErrorBadParameter;
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t bps = e->bps;
+    const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
+    // chroma on its own stream: copies and the two resizes overlap the luma kernel
+    if (chroma) {
+        const void *src[2] = {in_u, in_v};
+        const size_t sstep[2] = {in_u_step, in_v_step};
+        void *dst[2] = {out_u, out_v};
+        const size_t dstep[2] = {out_u_step, out_v_step};
+        for (int i = 0; i < 2; ++i) {
+            CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                      cudaMemcpyHostToDevice, e->stream_uv));
+            int rc = launch_resize(e, e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->stream_uv);
+            if (rc) return rc;
+            CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
+                                      cudaMemcpyDeviceToHost, e->stream_uv));
+        }
+    }
+    CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    int rc = raisr_cuda_process_device_rows(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, blending, 0,
+                                            e->out_h, e->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
+    return RNLErrorNone;
+}
+
+int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count)
+{
+    if (!e || pass < 0 || pass > 1 || !e->d_hash[pass] || !host_out) return RNLErrorBadParameter;
+    if (count != (size_t)e->hash_w[pass] * e->hash_h[pass]) return RNLErrorBadParameter;
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, e->d_hash[pass], count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return RNLErrorNone;
+}
+
+unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e) { return e ? e->launches : 0; }
+
+void raisr_cuda_destroy(raisr_cuda_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_hash[i]); }
+    for (int i = 0; i < 4; ++i) cudaFree(e->d_lut[i]);
+    for (int i = 0; i < 3; ++i) { e->d_in[i].release(); e->d_out[i].release(); }
+    e->d_mid.release();
+    e->yx.release(); e->yy.release(); e->cx.release(); e->cy.release();
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream_uv) cudaStreamDestroy(e->stream_uv);
+    if (e->ev_uv) cudaEventDestroy(e->ev_uv);
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    delete e;
+}
+
+}  // extern "C"
