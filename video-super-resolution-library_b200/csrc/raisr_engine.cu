@@ -118,6 +118,7 @@ struct raisr_cuda_engine {
     int bps = 1;                    // bytes per sample
     int lo = 0, hi = 255;
     int device = 0;
+    int num_sms = 148;
     float *d_filters[2] = {nullptr, nullptr};
     uint16_t *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};
     // geometry
@@ -163,8 +164,15 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
         CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_done = true;
     }
-    const dim3 grid((p.W + TW - 1) / TW, (p.row1 - p.row0 + TH - 1) / TH);
-    raisr_pass_kernel<PixT><<<grid, NT, SMEM_BYTES, s>>>(p);
+    // tile height: the largest th <= TH_MAX whose tile count just fills whole waves of the SMs (one CTA per SM)
+    PassParams q = p;
+    const int rows = p.row1 - p.row0, gx = (p.W + TW - 1) / TW;
+    int ny = (rows + TH_MAX - 1) / TH_MAX;
+    const int waves = (gx * ny + e->num_sms - 1) / e->num_sms;
+    while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && ny + 1 <= rows) ++ny;
+    q.tile_h = (rows + ny - 1) / ny;
+    const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
+    raisr_pass_kernel<PixT><<<grid, NT, SMEM_BYTES, s>>>(q);
     CUDA_OK(cudaGetLastError());
     e->launches++;
     return 0;
@@ -193,6 +201,7 @@ void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
     const PassModel &pm = e->model.pass[pass_idx];
     p->filters = e->d_filters[pass_idx];
     p->ptypes = pm.ptypes;
+    p->nbuckets = pm.buckets;
     p->qstr0 = pm.qstr[0]; p->qstr1 = pm.qstr[1];
     p->qcoh0 = pm.qcoh[0]; p->qcoh1 = pm.qcoh[1];
     p->lo = e->lo; p->hi = e->hi;
@@ -310,10 +319,26 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         }
     }
     if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
+    cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
     for (unsigned i = 0; i < passes; ++i) {
-        const size_t bytes = e->model.pass[i].filters.size() * sizeof(float);
+        // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
+        // contiguous bytes per step: tap k = 16m + j  ->  position (m/2)*32 + (j/2)*4 + (m%2)*2 + (j%2)   (see dot8())
+        const PassModel &pm = e->model.pass[i];
+        if (pm.buckets > NBUCKET_MAX) {
+            std::cout << "[RAISR ERROR] HashTable format is not compatible in number of hash keys!\n" << pm.buckets << std::endl;
+            return fail(RNLErrorBadParameter);
+        }
+        std::vector<float> dev((size_t)pm.ptypes * pm.buckets * 128, 0.0f);
+        for (int h = 0; h < pm.buckets; ++h)
+            for (int t = 0; t < pm.ptypes; ++t)
+                for (int k = 0; k < kTaps; ++k) {
+                    const int m = k / 16, j = k % 16;
+                    const int pos = (m / 2) * 32 + (j / 2) * 4 + (m % 2) * 2 + (j % 2);
+                    dev[((size_t)t * pm.buckets + h) * 128 + pos] = pm.filters[((size_t)h * pm.ptypes + t) * kTapStride + k];
+                }
+        const size_t bytes = dev.size() * sizeof(float);
         if (cudaMalloc(&e->d_filters[i], bytes) != cudaSuccess ||
-            cudaMemcpy(e->d_filters[i], e->model.pass[i].filters.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            cudaMemcpy(e->d_filters[i], dev.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(RNLErrorInsufficientResources);
     }
     if (e->cfg.numerics == RAISR_NUMERICS_X86_IF_AVAILABLE) {

@@ -1,11 +1,13 @@
 // raisr_kernels.cuh -- sm_100a device code of the RAISR luma pass and the chroma resize.
 //
-// One fused kernel per pass: a CTA owns a TW x TH tile of the pass's output plane and runs, entirely out
+// One fused kernel per pass: a CTA owns a TW x th tile of the pass's output plane and runs, entirely out
 // of shared memory,
 //   A  cheap upscale (exact-rational bilinear) or plain load of the integer input -> S tile (+7 halo)
-//   B  structure-tensor column chains                                              -> Q chunk
-//   C  per pixel: 11-lane tree sums -> eigen-analysis -> bucket; 121-tap filter    -> HR tile (+1 halo)
-//   D  3x3 census blend, round, clamp, store
+//   B  structure-tensor column chains, 8 rows at a time                            -> Q chunk
+//   C  per pixel: 11-lane tree sums -> eigen-analysis -> bucket                    -> bucket tile (+1 halo)
+//   D  per pixel type: TMA-bulk-load that type's 110 KB filter slice into shared memory, then the 121-tap
+//      filter with 8 lanes per pixel (conflict-free 128-byte reads of the selected filter row)  -> HR tile
+//   E  3x3 census blend, round, clamp, store
 // Arithmetic follows the reference's fp32 AVX-512 path rounding for rounding (file:line citations are
 // relative to /root/reference/Library); the organisation of the work does not.
 //
@@ -34,8 +36,10 @@ struct PassParams {
     const int *xw;           // [W] numerator of the right tap's weight over denx
     const int *ymap, *yw;    // same for rows, over deny
     int denx, deny;
-    const float *filters;    // [216][ptypes][128]
+    const float *filters;    // [ptypes][nbuckets][128]: per-type slices, rows lane-permuted for dot8()
     int ptypes;              // 4 or 1
+    int nbuckets;            // 216
+    int tile_h;              // output rows per CTA tile, <= TH_MAX
     float qstr0, qstr1, qcoh0, qcoh1;
     int lo, hi;              // colour range
     int c_end;               // hashed columns are [6, c_end)                  (Raisr.cpp:1065-1066)
@@ -53,20 +57,34 @@ struct PassParams {
 __constant__ float c_gw[11][6];
 
 // ---- tile geometry -------------------------------------------------------------------------------
-constexpr int NT = 256;          // threads per CTA
+constexpr int NT = 512;          // threads per CTA (one CTA per SM: the filter slice alone is 110 KB)
 constexpr int TW = 116;          // output tile width  (TW + 12 == 128 chain columns)
-constexpr int TH = 62;           // output tile height (TH + 2  == 64 filtered rows)
-constexpr int RB = 4;            // filtered rows per chunk
+constexpr int TH_MAX = 62;       // output tile height is chosen per launch, <= TH_MAX (TH_MAX + 2 == 64 filtered rows)
+constexpr int RB = 8;            // filtered rows per chunk
 constexpr int QW = TW + 12;      // chain columns per row
 constexpr int HW = TW + 2;       // filtered (HR) columns per row
 constexpr int SW = TW + 14;      // S tile columns
 constexpr int SP = SW + 2;       // S tile pitch (floats)
-constexpr int SH = TH + 14;      // S tile rows
+constexpr int SH = TH_MAX + 14;  // S tile rows
 constexpr int HP = HW + 2;       // HR tile pitch
-constexpr int HH = TH + 2;       // HR tile rows
+constexpr int HH = TH_MAX + 2;   // HR tile rows
 constexpr int GR = RB + 10;      // gradient rows per chunk
-constexpr size_t SMEM_BYTES = sizeof(float) * ((size_t)SH * SP + (size_t)HH * HP + 2u * GR * QW + (size_t)RB * 18 * QW);
+constexpr int NBUCKET_MAX = 216;
+constexpr int SLICE_FLOATS = NBUCKET_MAX * 128;                 // one pixel type's filters, lane-permuted rows of 128 floats
+constexpr int OVW = 8;                                          // width of the 16-wide/8-wide hash overlap (Raisr.cpp:1247-1250)
+// shared memory carve-up (bytes).  The chunk buffers of stages B/C live inside the filter-slice buffer, which is
+// only filled (by cp.async.bulk) once all chunks are done.
+constexpr size_t OFF_S = 0;
+constexpr size_t OFF_HR = OFF_S + sizeof(float) * SH * SP;
+constexpr size_t OFF_F = (OFF_HR + sizeof(float) * HH * HP + 127) & ~(size_t)127;
+constexpr size_t OFF_HASH = OFF_F + sizeof(float) * SLICE_FLOATS;
+constexpr size_t OFF_HASH2 = OFF_HASH + (size_t)HH * HP;
+constexpr size_t OFF_MBAR = (OFF_HASH2 + (size_t)HH * OVW + 15) & ~(size_t)15;
+constexpr size_t SMEM_BYTES = OFF_MBAR + 16;
 static_assert(QW == 128 && HH % RB == 0, "tile geometry");
+static_assert(sizeof(float) * (2u * GR * QW + (size_t)RB * 18 * QW) <= sizeof(float) * SLICE_FLOATS, "chunk buffers must fit in the slice buffer");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_F % 128 == 0, "slice buffer alignment");
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -218,53 +236,90 @@ __device__ __forceinline__ float tree_sum_B(const float *k)
     return fadd(fadd(t40, t42), fadd(t41, t43));
 }
 
-// 121-tap filter in the reference's order: 16 lane chains over 8 chunks, then the tree
-// (DotProdPatch_AVX512_32f, Raisr_AVX512.cpp:134-149).  sp = &S[r-5][c-5] in the shared tile.
-__device__ __forceinline__ float dot_patch(const float *sp, const float *__restrict__ f)
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX) ---------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
 {
-    float acc[16];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 121-tap filter in the reference's order -- 16 lane chains over 8 chunks of 16 taps, then the 16-lane tree
+// (DotProdPatch_AVX512_32f, Raisr_AVX512.cpp:134-149) -- evaluated by 8 GPU lanes per pixel: lane q owns chains 2q
+// and 2q+1.  frow = the pixel's filter row in the slice buffer, stored lane-permuted as [n][q][4] =
+// {tap(16*2n + 2q), tap(16*2n + 2q+1), tap(16*(2n+1) + 2q), tap(16*(2n+1) + 2q+1)}, so the 8 lanes of a pixel read
+// 128 contiguous bytes per n (conflict-free) and 4 pixels per warp proceed in lock step.
+// sp = &S[r-5][c-5]; off[m][e] = offset of tap 16m + 2q + e inside the patch (0 with a zero coefficient for taps >= 121).
+__device__ __forceinline__ float dot8(const float *sp, const float *frow, const int (&off)[8][2], int q)
+{
+    float a0 = 0.0f, a1 = 0.0f;
+    const float4 *f4 = reinterpret_cast<const float4 *>(frow) + q;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        float fv[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(f + 16 * m + 4 * q));
-            fv[4 * q] = v.x; fv[4 * q + 1] = v.y; fv[4 * q + 2] = v.z; fv[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int k = 16 * m + j;
-            if (k < 121) {
-                const float pv = sp[(k / 11) * SP + (k % 11)];
-                acc[j] = (m == 0) ? fmul(pv, fv[j]) : ffma(pv, fv[j], acc[j]);
-            }
-        }
+    for (int n = 0; n < 4; ++n) {
+        const float4 f = f4[n * 8];
+        const float p0 = sp[off[2 * n][0]], p1 = sp[off[2 * n][1]];
+        const float p2 = sp[off[2 * n + 1][0]], p3 = sp[off[2 * n + 1][1]];
+        if (n == 0) { a0 = fmul(p0, f.x); a1 = fmul(p1, f.y); }
+        else { a0 = ffma(p0, f.x, a0); a1 = ffma(p1, f.y, a1); }
+        a0 = ffma(p2, f.z, a0);
+        a1 = ffma(p3, f.w, a1);
     }
-    float t8[8], t4[4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t8[j] = fadd(acc[j], acc[j + 8]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t4[j] = fadd(t8[j], t8[j + 4]);
-    return fadd(fadd(t4[0], t4[2]), fadd(t4[1], t4[3]));
+    // tree: t8[j] = acc[j] + acc[j+8] (lane q <- q+4); t4[j] = t8[j] + t8[j+4] (q <- q+2); t2[j] = t4[j] + t4[j+2] (q <- q+1)
+    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 4, 8));
+    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 4, 8));
+    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 2, 8));
+    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 2, 8));
+    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 1, 8));
+    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 1, 8));
+    return fadd(a0, a1);          // valid in lane q == 0
 }
 
 template <typename PixT>
 __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
 {
-    extern __shared__ float smem[];
-    float *sS = smem;                       // [SH][SP]   S rows  y0-7 .. y0+TH+6, cols x0-7 .. x0+TW+6
-    float *sHR = sS + SH * SP;              // [HH][HP]   HR rows y0-1 .. y0+TH,   cols x0-1 .. x0+TW
-    float *sGX = sHR + HH * HP;             // [GR][QW]
-    float *sGY = sGX + GR * QW;             // [GR][QW]
-    float *sQ = sGY + GR * QW;              // [RB][18][QW]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sS = reinterpret_cast<float *>(smem_raw + OFF_S);      // [SH][SP]  S rows  y0-7 .. , cols x0-7 .. x0+TW+6
+    float *sHR = reinterpret_cast<float *>(smem_raw + OFF_HR);    // [HH][HP]  HR rows y0-1 .. , cols x0-1 .. x0+TW
+    float *sF = reinterpret_cast<float *>(smem_raw + OFF_F);      // filter slice; before that: chunk buffers
+    float *sGX = sF;                                              // [GR][QW]
+    float *sGY = sGX + GR * QW;                                   // [GR][QW]
+    float *sQ = sGY + GR * QW;                                    // [RB][18][QW]
+    unsigned char *sHash = smem_raw + OFF_HASH;                   // [HH][HP] bucket, 255 = not hashed
+    unsigned char *sHash2 = smem_raw + OFF_HASH2;                 // [HH][OVW] 16-wide bucket of overlap columns, 255 = same
+    void *mbar = smem_raw + OFF_MBAR;
 
     const int tid = threadIdx.x;
+    const int th = p.tile_h;
     const int x0 = blockIdx.x * TW;
-    const int y0 = p.row0 + blockIdx.y * TH;
+    const int y0 = p.row0 + blockIdx.y * th;
     const int W = p.W, H = p.H;
+    const int hh = th + 2;                                        // filtered rows of this tile
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     // ---- A: S tile ---------------------------------------------------------------------------------
-    for (int idx = tid; idx < SH * SW; idx += NT) {
+    for (int idx = tid; idx < (th + 14) * SW; idx += NT) {
         const int sy = idx / SW, sx = idx - sy * SW;
         const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
         float v = 0.0f;
@@ -276,17 +331,14 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.lut_rsqrt14, p.lut_rcp14, p.lut_rsqrtps, p.lut_rcpps};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 
-    for (int ch = 0; ch < HH / RB; ++ch) {
-        const int h0 = ch * RB;                               // first HR-tile row of the chunk
-        const int rfirst = y0 - 1 + h0;                       // its frame row
-        // rows of this chunk that are hashed at all (uniform per CTA)
+    for (int h0 = 0; h0 < hh; h0 += RB) {
+        const int rfirst = y0 - 1 + h0;                       // frame row of the chunk's first filtered row
         const bool any_hashed = (rfirst + RB > 6) && (rfirst < H - 6) && (x0 - 1 + HW > 6) && (x0 - 1 < p.c_end);
         if (any_hashed) {
-            // gradients for S rows h0+1 .. h0+RB+10, chain columns q <-> S col q+1
+            // gradients for S rows h0+1 .. h0+RB+10, chain column q <-> S col q+1
             for (int idx = tid; idx < GR * QW; idx += NT) {
                 const int g = idx / QW, q = idx - g * QW;
-                const int srow = h0 + 1 + g;
-                const float *s = sS + srow * SP + q + 1;
+                const float *s = sS + (h0 + 1 + g) * SP + q + 1;
                 sGX[idx] = fsub(s[SP], s[-SP]);               // GetGx: next row - previous row (Raisr_AVX512.cpp:54-57)
                 sGY[idx] = fsub(s[1], s[-1]);                 // GetGy: right - left            (Raisr_AVX512.cpp:59-62)
             }
@@ -294,6 +346,8 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
             // ---- B: column chains ---------------------------------------------------------------------
             for (int it = tid; it < RB * QW; it += NT) {
                 const int rl = it / QW, q = it - rl * QW;
+                const int r = rfirst + rl;
+                if (r < 6 || r >= H - 6 || h0 + rl >= hh) continue;
                 float acc[6][3];
 #pragma unroll
                 for (int m = 0; m < 6; ++m) acc[m][0] = acc[m][1] = acc[m][2] = 0.0f;
@@ -317,14 +371,13 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
             }
             __syncthreads();
         }
-        // ---- C: bucket + filter ---------------------------------------------------------------------
+        // ---- C: bucket ------------------------------------------------------------------------------
         for (int it = tid; it < RB * QW; it += NT) {
             const int rl = it / QW, j = it - rl * QW;
-            if (j >= HW) continue;
-            const int r = rfirst + rl, c = x0 - 1 + j;
             const int h = h0 + rl;
-            const float sc = sS[(h + 6) * SP + j + 6];
-            float hr = sc;
+            if (j >= HW || h >= hh) continue;
+            const int r = rfirst + rl, c = x0 - 1 + j;
+            int hv = 255, hv2 = 255;
             if (any_hashed && r >= 6 && r < H - 6 && c >= 6 && c < p.c_end) {
                 float g[3];
                 const float *qs = sQ + (rl * 18) * QW + j;
@@ -338,34 +391,86 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     }
                     g[k3] = (c & 1) ? tree_sum_B(lane) : tree_sum_A(lane);
                 }
-                const int pt = (p.ptypes == 4) ? ((((r - 5) & 1) << 1) | ((c - 5) & 1)) : 0;     // Raisr.cpp:1068-1096
-                const float *sp = sS + (h + 1) * SP + j + 1;
-                int hv;
                 if (c < p.tail_start) {
                     hv = hash_bucket<true>(hc, g[0], g[1], g[2]);
-                    const float cur = dot_patch(sp, p.filters + ((size_t)hv * p.ptypes + pt) * 128);
-                    if (cur > flo && cur < fhi) hr = cur;                                        // Raisr.cpp:1192-1196
                 } else {
                     hv = hash_bucket<false>(hc, g[0], g[1], g[2]);
-                    if (c < p.ov_end) {       // first pass of the overlap: 16-wide hash (kept if the 8-wide result is invalid)
-                        const int hv16 = hash_bucket<true>(hc, g[0], g[1], g[2]);
-                        if (hv16 != hv) {
-                            const float cur16 = dot_patch(sp, p.filters + ((size_t)hv16 * p.ptypes + pt) * 128);
-                            if (cur16 > flo && cur16 < fhi) hr = cur16;
-                        }
+                    if (c < p.ov_end) {     // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
+                        const int h16 = hash_bucket<true>(hc, g[0], g[1], g[2]);
+                        if (h16 != hv) hv2 = h16;
                     }
-                    const float cur = dot_patch(sp, p.filters + ((size_t)hv * p.ptypes + pt) * 128);
-                    if (cur > flo && cur < fhi) hr = cur;
                 }
                 if (p.hash_out && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
             }
-            sHR[h * HP + j] = hr;
+            sHash[h * HP + j] = (unsigned char)hv;
+            if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
+            sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
         }
         __syncthreads();
     }
 
-    // ---- D: census blend + store (CTCountOfBitsChangedSegment_AVX256_32f, Raisr_AVX256.cpp:68-166) ----
-    for (int idx = tid; idx < TH * TW; idx += NT) {
+    // ---- D: 121-tap filter, one pixel type at a time ----------------------------------------------------------
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int g = lane >> 3, q = lane & 7;
+        int off[8][2];
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 16 * m + 2 * q + e;
+                off[m][e] = (k < 121) ? (k / 11) * SP + (k % 11) : 0;
+            }
+        const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
+        const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
+        for (int t = 0; t < p.ptypes; ++t) {
+            if (tid == 0) {
+                fence_proxy_async();                              // generic-proxy accesses to the buffer are done (barrier above)
+                mbar_expect_tx(mbar, (unsigned)slice_bytes);
+                const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
+                const int piece = slice_bytes / 4;                // 4 bulk copies (each a multiple of 16 bytes)
+                for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mbar);
+            }
+            // pixels of type t inside the HR tile: frame parity (r-5)&1 == t>>1, (c-5)&1 == t&1   (Raisr.cpp:1068-1096)
+            int jfirst, hfirst, jstep, hstep;
+            if (p.ptypes == 4) {
+                jstep = hstep = 2;
+                jfirst = ((x0 - 1 - 5) & 1) == (t & 1) ? 0 : 1;
+                hfirst = ((y0 - 1 - 5) & 1) == (t >> 1) ? 0 : 1;
+            } else {
+                jstep = hstep = 1; jfirst = hfirst = 0;
+            }
+            const int ncols = (HW - jfirst + jstep - 1) / jstep;
+            const int ngrp = (ncols + 3) >> 2;                    // groups of 4 pixels along a row
+            const int nrows = (hh - hfirst + hstep - 1) / hstep;
+            mbar_wait(mbar, (unsigned)(t & 1));
+            for (int it = warp; it < nrows * ngrp; it += NT / 32) {
+                const int ri = it / ngrp, gi = it - ri * ngrp;
+                const int h = hfirst + ri * hstep;
+                const int jc = jfirst + (gi * 4 + g) * jstep;
+                const int j = min(jc, HW - 1);                    // clamp: lanes past the row end recompute the last pixel
+                const int hv = sHash[h * HP + j];
+                const float *sp = sS + (h + 1) * SP + j + 1;
+                const float cur = dot8(sp, sF + (hv == 255 ? 0 : hv) * 128, off, q);
+                bool ok = (cur > flo) && (cur < fhi);             // strict range test, Raisr.cpp:1192-1196
+                float res = cur;
+                if (has_ov) {
+                    const int c = x0 - 1 + j;
+                    const int hv2 = (c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
+                    const bool need2 = (hv2 != 255) && !ok;
+                    if (__any_sync(0xffffffffu, need2)) {
+                        const float cur16 = dot8(sp, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
+                        if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
+                    }
+                }
+                if (q == 0 && jc < HW && hv != 255 && ok) sHR[h * HP + j] = res;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- E: census blend + store (CTCountOfBitsChangedSegment_AVX256_32f, Raisr_AVX256.cpp:68-166) ----
+    for (int idx = tid; idx < th * TW; idx += NT) {
         const int ty = idx / TW, tx = idx - ty * TW;
         const int Y = y0 + ty, X = x0 + tx;
         if (Y >= p.row1 || Y >= H || X >= W) continue;
