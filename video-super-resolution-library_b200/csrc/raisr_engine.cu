@@ -125,6 +125,7 @@ struct raisr_cuda_engine {
     bool have_res = false;
     int in_w = 0, in_h = 0, out_w = 0, out_h = 0, in_cw = 0, in_ch = 0, out_cw = 0, out_ch = 0;
     AxisMap yx, yy, cx, cy;
+    int up_src_h = 0;
     Plane d_in[3], d_out[3], d_mid;
     int *d_hash[2] = {nullptr, nullptr};
     int hash_w[2] = {0, 0}, hash_h[2] = {0, 0};
@@ -156,26 +157,43 @@ int fill_weights(unsigned bits)
     return 0;
 }
 
-template <typename PixT>
-int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
+template <typename PixT, int PT, int UPS>
+int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStream_t s)
 {
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_done = true;
     }
-    // tile height: the largest th <= TH_MAX whose tile count just fills whole waves of the SMs (one CTA per SM)
+    raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+template <typename PixT>
+int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
+{
+    // tile height: the largest even th <= TH_MAX whose tile count still fits the same number of waves (one CTA per SM)
     PassParams q = p;
     const int rows = p.row1 - p.row0, gx = (p.W + TW - 1) / TW;
     int ny = (rows + TH_MAX - 1) / TH_MAX;
     const int waves = (gx * ny + e->num_sms - 1) / e->num_sms;
-    while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && ny + 1 <= rows) ++ny;
-    q.tile_h = (rows + ny - 1) / ny;
+    while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && 2 * (ny + 1) <= rows) ++ny;
+    q.tile_h = std::min(TH_MAX, (((rows + ny - 1) / ny) + 1) & ~1);
     const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
-    raisr_pass_kernel<PixT><<<grid, NT, SMEM_BYTES, s>>>(q);
-    CUDA_OK(cudaGetLastError());
-    e->launches++;
-    return 0;
+    q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch) % (4 * sizeof(PixT))) == 0;
+    // 2x fast path: exact factor 2 in both axes and even band origin
+    const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
+    const int ups = !p.upscale ? 0 : (fast2x ? 1 : 2);
+    if (p.ptypes == 4) {
+        if (ups == 0) return launch_pass_k<PixT, 4, 0>(e, q, grid, s);
+        if (ups == 1) return launch_pass_k<PixT, 4, 1>(e, q, grid, s);
+        return launch_pass_k<PixT, 4, 2>(e, q, grid, s);
+    }
+    if (ups == 0) return launch_pass_k<PixT, 1, 0>(e, q, grid, s);
+    if (ups == 1) return launch_pass_k<PixT, 1, 1>(e, q, grid, s);
+    return launch_pass_k<PixT, 1, 2>(e, q, grid, s);
 }
 
 int launch_pass(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
@@ -219,6 +237,7 @@ void set_upscale(const raisr_cuda_engine *e, PassParams *p)
     p->upscale = 1;
     p->xmap = e->yx.d_map; p->xw = e->yx.d_w; p->ymap = e->yy.d_map; p->yw = e->yy.d_w;
     p->denx = e->yx.den; p->deny = e->yy.den;
+    p->up_src_h = e->up_src_h;
 }
 
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
@@ -382,6 +401,7 @@ int raisr_cuda_set_res(raisr_cuda_engine *e, unsigned in_w, unsigned in_h, unsig
     if (src_h < 1) src_h = 1;
     e->yx.build(in_w, out_w);
     e->yy.build(src_h, out_h);
+    e->up_src_h = src_h;
     if (e->yx.upload() || e->yy.upload()) return RNLErrorInsufficientResources;
     if (in_cw && in_ch && out_cw && out_ch) {
         e->cx.build(in_cw, out_cw);

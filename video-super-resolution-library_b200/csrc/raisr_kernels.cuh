@@ -36,10 +36,12 @@ struct PassParams {
     const int *xw;           // [W] numerator of the right tap's weight over denx
     const int *ymap, *yw;    // same for rows, over deny
     int denx, deny;
+    int up_src_h;            // source rows the vertical map was built for
     const float *filters;    // [ptypes][nbuckets][128]: per-type slices, rows lane-permuted for dot8()
     int ptypes;              // 4 or 1
     int nbuckets;            // 216
-    int tile_h;              // output rows per CTA tile, <= TH_MAX
+    int tile_h;              // output rows per CTA tile, <= TH_MAX (even)
+    int vec_store;           // output base and pitch allow 4-pixel vector stores
     float qstr0, qstr1, qcoh0, qcoh1;
     int lo, hi;              // colour range
     int c_end;               // hashed columns are [6, c_end)                  (Raisr.cpp:1065-1066)
@@ -64,7 +66,7 @@ constexpr int RB = 8;            // filtered rows per chunk
 constexpr int QW = TW + 12;      // chain columns per row
 constexpr int HW = TW + 2;       // filtered (HR) columns per row
 constexpr int SW = TW + 14;      // S tile columns
-constexpr int SP = SW + 2;       // S tile pitch (floats)
+constexpr int SP = 142;          // S tile pitch (floats): makes the 16 patch loads of dot8() bank-conflict free at column stride 1 and 2
 constexpr int SH = TH_MAX + 14;  // S tile rows
 constexpr int HP = HW + 2;       // HR tile pitch
 constexpr int HH = TH_MAX + 2;   // HR tile rows
@@ -81,7 +83,8 @@ constexpr size_t OFF_HASH = OFF_F + sizeof(float) * SLICE_FLOATS;
 constexpr size_t OFF_HASH2 = OFF_HASH + (size_t)HH * HP;
 constexpr size_t OFF_MBAR = (OFF_HASH2 + (size_t)HH * OVW + 15) & ~(size_t)15;
 constexpr size_t SMEM_BYTES = OFF_MBAR + 16;
-static_assert(QW == 128 && HH % RB == 0, "tile geometry");
+static_assert(QW == 128 && HH % RB == 0 && SP >= SW && TW % 4 == 0 && HP % 4 == 0, "tile geometry");
+constexpr int LRW = SW / 2 + 1, LRP = LRW + 1;   // low-res tile of the 2x fast path (lives in the slice buffer during stage A)
 static_assert(sizeof(float) * (2u * GR * QW + (size_t)RB * 18 * QW) <= sizeof(float) * SLICE_FLOATS, "chunk buffers must fit in the slice buffer");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_F % 128 == 0, "slice buffer alignment");
@@ -93,9 +96,9 @@ __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf
 
 // ---- stage A: one sample of the cheap upscale (oracle/ipp_standin/ipp.h semantics) -----------------
 template <typename PixT>
-__device__ __forceinline__ float load_S(const PassParams &p, int Y, int X)
+__device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool upscale)
 {
-    if (!p.upscale) {
+    if (!upscale) {
         const PixT *row = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)Y * p.in_pitch);
         return (float)row[X];
     }
@@ -292,7 +295,9 @@ __device__ __forceinline__ float dot8(const float *sp, const float *frow, const 
     return fadd(a0, a1);          // valid in lane q == 0
 }
 
-template <typename PixT>
+// UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),
+//      2 = any ratio through the per-axis tables (1.5x).   PT: pixel types (4 at 2x, else 1).
+template <typename PixT, int PT, int UPS>
 __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -319,12 +324,47 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     }
 
     // ---- A: S tile ---------------------------------------------------------------------------------
-    for (int idx = tid; idx < (th + 14) * SW; idx += NT) {
-        const int sy = idx / SW, sx = idx - sy * SW;
-        const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
-        float v = 0.0f;
-        if (Y >= 0 && Y < H && X >= 0 && X < W) v = load_S<PixT>(p, Y, X);
-        sS[sy * SP + sx] = v;
+    if (UPS == 1) {
+        // low-res tile (replicate border = clamped coordinates), then every low-res sample's 3x3 neighbourhood yields the
+        // 2x2 outputs (2j, 2j+1): even outputs weigh (j-1, j) by (1,3), odd outputs (j, j+1) by (3,1); all sums are exact
+        // integers < 2^24, so fp32 evaluates (9a+3b+3c+d+8)>>4 exactly (oracle/ipp_standin/ipp.h).
+        float *sL = sF;
+        const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;       // x0, y0 even
+        const int lrh = (th + 14) / 2 + 1;
+        for (int idx = tid; idx < lrh * LRW; idx += NT) {
+            const int ly = idx / LRW, lx = idx - ly * LRW;
+            const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
+            sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
+        }
+        __syncthreads();
+        // block (bi,bj) centred on low-res (bi,bj) emits S rows 2bi-1, 2bi and cols 2bj-1, 2bj (tile-local)
+        for (int idx = tid; idx < (lrh - 1) * (LRW - 1); idx += NT) {
+            const int bi = idx / (LRW - 1) + 1, bj = idx - (bi - 1) * (LRW - 1) + 1;
+            const float *l = sL + bi * LRP + bj;
+            const float a0 = l[-LRP - 1], a1 = l[-LRP], a2 = l[-LRP + 1];
+            const float b0 = l[-1], b1 = l[0], b2 = l[1];
+            // even output row 2j: rows (j-1, j) x (1,3);  here row 2bi-2.. handled as: S row (2bi-1) is odd output of low-res row bi-1?
+            // tile-local S row sy <-> Y = y0-7+sy; Y odd for even sy.  Output Y=2j+1 (odd) uses rows (j, j+1) x (3,1); Y=2j uses (j-1, j) x (1,3).
+            // Low-res row index of l[0] is j = ly0 + bi.  S row for Y=2j   : sy = 2j - (y0-7) = 2bi - 1.  S row for Y=2j-1 (odd, rows (j-1,j) x (3,1)): sy = 2bi - 2.
+            const float vo0 = ffma(3.0f, a0, b0), vo1 = ffma(3.0f, a1, b1), vo2 = ffma(3.0f, a2, b2);     // Y = 2j-1: 3*row(j-1) + row(j)
+            const float ve0 = ffma(3.0f, b0, a0), ve1 = ffma(3.0f, b1, a1), ve2 = ffma(3.0f, b2, a2);     // Y = 2j  : row(j-1) + 3*row(j)
+            // columns likewise: X = 2i-1 (odd): 3*col(i-1) + col(i);  X = 2i: col(i-1) + 3*col(i);  sx = 2bj-2, 2bj-1
+            const int sy = 2 * bi - 2, sx = 2 * bj - 2;
+            float *d = sS + sy * SP + sx;
+            d[0] = floorf(fmul(fadd(ffma(3.0f, vo0, vo1), 8.0f), 0.0625f));
+            d[1] = floorf(fmul(fadd(ffma(3.0f, vo1, vo0), 8.0f), 0.0625f));
+            d[SP] = floorf(fmul(fadd(ffma(3.0f, ve0, ve1), 8.0f), 0.0625f));
+            d[SP + 1] = floorf(fmul(fadd(ffma(3.0f, ve1, ve0), 8.0f), 0.0625f));
+            (void)vo2; (void)ve2;
+        }
+    } else {
+        for (int idx = tid; idx < (th + 14) * SW; idx += NT) {
+            const int sy = idx / SW, sx = idx - sy * SW;
+            const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
+            float v = 0.0f;
+            if (Y >= 0 && Y < H && X >= 0 && X < W) v = load_S<PixT>(p, Y, X, UPS != 0);
+            sS[sy * SP + sx] = v;
+        }
     }
     __syncthreads();
 
@@ -411,6 +451,10 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
 
     // ---- D: 121-tap filter, one pixel type at a time ----------------------------------------------------------
     {
+        constexpr int JS = (PT == 4) ? 2 : 1;                     // column/row stride between pixels of one type
+        constexpr int U = 4;                                      // pixel groups per warp iteration (one group = 4 pixels x 8 lanes)
+        constexpr int NCOLS = (HW + JS - 1) / JS;                 // upper bound of same-type columns in a tile row
+        constexpr int NBLK = (NCOLS + 4 * U - 1) / (4 * U);       // warp iterations per row
         const int lane = tid & 31, warp = tid >> 5;
         const int g = lane >> 3, q = lane & 7;
         int off[8][2];
@@ -423,7 +467,8 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
             }
         const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
         const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
-        for (int t = 0; t < p.ptypes; ++t) {
+        const float4 *sF4 = reinterpret_cast<const float4 *>(sF) + q;
+        for (int t = 0; t < PT; ++t) {
             if (tid == 0) {
                 fence_proxy_async();                              // generic-proxy accesses to the buffer are done (barrier above)
                 mbar_expect_tx(mbar, (unsigned)slice_bytes);
@@ -432,70 +477,101 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                 for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mbar);
             }
             // pixels of type t inside the HR tile: frame parity (r-5)&1 == t>>1, (c-5)&1 == t&1   (Raisr.cpp:1068-1096)
-            int jfirst, hfirst, jstep, hstep;
-            if (p.ptypes == 4) {
-                jstep = hstep = 2;
-                jfirst = ((x0 - 1 - 5) & 1) == (t & 1) ? 0 : 1;
-                hfirst = ((y0 - 1 - 5) & 1) == (t >> 1) ? 0 : 1;
-            } else {
-                jstep = hstep = 1; jfirst = hfirst = 0;
-            }
-            const int ncols = (HW - jfirst + jstep - 1) / jstep;
-            const int ngrp = (ncols + 3) >> 2;                    // groups of 4 pixels along a row
-            const int nrows = (hh - hfirst + hstep - 1) / hstep;
+            const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;
+            const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
+            const int nrows = (hh - hfirst + JS - 1) / JS;
             mbar_wait(mbar, (unsigned)(t & 1));
-            for (int it = warp; it < nrows * ngrp; it += NT / 32) {
-                const int ri = it / ngrp, gi = it - ri * ngrp;
-                const int h = hfirst + ri * hstep;
-                const int jc = jfirst + (gi * 4 + g) * jstep;
-                const int j = min(jc, HW - 1);                    // clamp: lanes past the row end recompute the last pixel
-                const int hv = sHash[h * HP + j];
-                const float *sp = sS + (h + 1) * SP + j + 1;
-                const float cur = dot8(sp, sF + (hv == 255 ? 0 : hv) * 128, off, q);
-                bool ok = (cur > flo) && (cur < fhi);             // strict range test, Raisr.cpp:1192-1196
-                float res = cur;
-                if (has_ov) {
-                    const int c = x0 - 1 + j;
-                    const int hv2 = (c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
-                    const bool need2 = (hv2 != 255) && !ok;
-                    if (__any_sync(0xffffffffu, need2)) {
-                        const float cur16 = dot8(sp, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
-                        if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
+            for (int it = warp; it < nrows * NBLK; it += NT / 32) {
+                const int ri = it / NBLK, bi = it - ri * NBLK;
+                const int h = hfirst + ri * JS;
+                const int jb = jfirst + (bi * 4 * U + g) * JS;    // column of this lane's pixel in group u = 0; group u is 4*JS*u further
+                const float *sp = sS + (h + 1) * SP + jb + 1;
+                const unsigned char *hp = sHash + h * HP + jb;
+                int hv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) hv[u] = (jb + 4 * JS * u < HW) ? hp[4 * JS * u] : 255;
+                float a0[U], a1[U];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float *q0 = sp + off[2 * n][0], *q1 = sp + off[2 * n][1], *q2 = sp + off[2 * n + 1][0], *q3 = sp + off[2 * n + 1][1];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float4 f = sF4[(hv[u] == 255 ? 0 : hv[u]) * 32 + n * 8];
+                        const float p0 = q0[4 * JS * u], p1 = q1[4 * JS * u], p2 = q2[4 * JS * u], p3 = q3[4 * JS * u];
+                        if (n == 0) { a0[u] = fmul(p0, f.x); a1[u] = fmul(p1, f.y); }
+                        else { a0[u] = ffma(p0, f.x, a0[u]); a1[u] = ffma(p1, f.y, a1[u]); }
+                        a0[u] = ffma(p2, f.z, a0[u]);
+                        a1[u] = ffma(p3, f.w, a1[u]);
                     }
                 }
-                if (q == 0 && jc < HW && hv != 255 && ok) sHR[h * HP + j] = res;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    // tree: t8[j] = acc[j]+acc[j+8] (lane q <- q+4); t4[j] = t8[j]+t8[j+4] (q <- q+2); t2[j] = t4[j]+t4[j+2] (q <- q+1)
+                    float x = a0[u], y = a1[u];
+                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 4, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 4, 8));
+                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 2, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 2, 8));
+                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 1, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 1, 8));
+                    const float cur = fadd(x, y);                 // valid in lane q == 0
+                    bool ok = (cur > flo) && (cur < fhi);         // strict range test, Raisr.cpp:1192-1196
+                    float res = cur;
+                    const int j = jb + 4 * JS * u;
+                    if (has_ov) {                                 // tile holds columns hashed by both variants (rare path)
+                        const int c = x0 - 1 + j;
+                        const int hv2 = (j < HW && c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
+                        const bool need2 = (hv2 != 255) && !ok;
+                        if (__any_sync(0xffffffffu, need2)) {
+                            const float cur16 = dot8(sp + 4 * JS * u, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
+                            if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
+                        }
+                    }
+                    if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
+                }
             }
             __syncthreads();
         }
     }
 
     // ---- E: census blend + store (CTCountOfBitsChangedSegment_AVX256_32f, Raisr_AVX256.cpp:68-166) ----
-    for (int idx = tid; idx < th * TW; idx += NT) {
-        const int ty = idx / TW, tx = idx - ty * TW;
+    // one thread = 4 consecutive pixels of a row: a 3x6 window of S and of HR, one vector store
+    for (int idx = tid; idx < th * (TW / 4); idx += NT) {
+        const int ty = idx / (TW / 4), tx = (idx - ty * (TW / 4)) * 4;
         const int Y = y0 + ty, X = x0 + tx;
         if (Y >= p.row1 || Y >= H || X >= W) continue;
-        const float *s = sS + (ty + 7) * SP + tx + 7;
-        const float *hq = sHR + (ty + 1) * HP + tx + 1;
-        const float lc = s[0], hcv = hq[0];
-        int iv;
-        if (Y == 0 || X == 0 || Y == H - 1 || X == W - 1) {
-            iv = (int)lc;                                           // 1-px frame: the integer upscale itself (Raisr.cpp:999-1028,1252-1265)
-        } else {
+        float sw[3][6], hw[3][6];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const float *s = sS + (ty + 6 + dy) * SP + tx + 6;
+            const float *hq = sHR + (ty + dy) * HP + tx;
+#pragma unroll
+            for (int dx = 0; dx < 6; ++dx) { sw[dy][dx] = s[dx]; hw[dy][dx] = hq[dx]; }
+        }
+        int iv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
             int ham = 0;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    if (dy == 0 && dx == 0) continue;
-                    ham += ((s[dy * SP + dx] < lc) != (hq[dy * HP + dx] < hcv));
+                for (int dx = 0; dx < 3; ++dx) {
+                    if (dy == 1 && dx == 1) continue;
+                    ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
                 }
             const float w = fmul((float)ham, 0.125f);
             const float v = fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f);
-            iv = (int)floorf(v);
-            iv = min(max(iv, p.lo), p.hi);
+            int r = min(max((int)floorf(v), p.lo), p.hi);
+            if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;   // 1-px frame: the integer upscale itself (Raisr.cpp:999-1028,1252-1265)
+            iv[e] = r;
         }
-        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch);
-        orow[X] = (PixT)iv;
+        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
+        if (p.vec_store && X + 3 < W) {
+            if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
+            else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (X + e < W) orow[e] = (PixT)iv[e];
+        }
     }
 }
 
@@ -521,7 +597,7 @@ __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams rp)
         const int Y = Yb + k;
         if (Y >= rp.H) break;
         PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(rp.out) + (size_t)Y * rp.out_pitch);
-        orow[X] = (PixT)(int)load_S<PixT>(p, Y, X);
+        orow[X] = (PixT)(int)load_S<PixT>(p, Y, X, true);
     }
 }
 
