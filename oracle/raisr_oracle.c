@@ -71,10 +71,17 @@ static void gtwg_pair(const float *F, int W, int r, int cA, const float wt[11][1
         const float *ra = base + (size_t)i * W;         /* row r-6+i  */
         const float *rb = ra + W;                       /* row r-5+i  (the patch row) */
         const float *rc = rb + W;                       /* row r-4+i  */
-        float gx[16], gy[16];
+        float gx[16], gy[16], va[16], vb[16], vc[16];
+        /* The 16-float row loads of the reference run up to 2 floats past the end of a row for the right-most pairs
+         * (and past the end of the buffer on the last hashed row).  Those lanes (14, 15) carry zero weight, so whatever
+         * finite value is there contributes an exact +0; the restatement reads 0 instead of stray memory. */
         for (int j = 0; j < 16; j++) {
-            gx[j] = rc[j] - ra[j];                                  /* GetGx: :54-57  */
-            gy[j] = rb[(j + 1) & 15] - rb[(j + 15) & 15];           /* GetGy: :59-62 (lane rotates) */
+            const int inb = (cA - 6 + j) < W;
+            va[j] = inb ? ra[j] : 0.0f; vb[j] = inb ? rb[j] : 0.0f; vc[j] = inb ? rc[j] : 0.0f;
+        }
+        for (int j = 0; j < 16; j++) {
+            gx[j] = vc[j] - va[j];                                  /* GetGx: :54-57  */
+            gy[j] = vb[(j + 1) & 15] - vb[(j + 15) & 15];           /* GetGy: :59-62 (lane rotates) */
         }
         for (int j = 0; j < 16; j++) {
             float wA = wt[i][j];
@@ -92,11 +99,6 @@ static void gtwg_pair(const float *F, int W, int r, int cA, const float wt[11][1
 }
 
 /* ---- hash (Raisr_AVX512.cpp:151-258 for 16-wide blocks, Raisr_AVX256.cpp:366-472 for 8-wide) - */
-typedef float (*sqrt_fn)(float);
-static float sqrt_ieee(float x) { return sqrtf(x); }
-static float sqrt_x86_14(float x) { return oracle_x86_rcp14(oracle_x86_rsqrt14(x)); }   /* Raisr_AVX512.cpp:200,221-222 */
-static float sqrt_x86_ps(float x) { return oracle_x86_rcpps(oracle_x86_rsqrtps(x)); }   /* Raisr_AVX256.cpp:419,441-442 */
-
 static float atan2_approx(float y, float x)     /* Raisr_AVX512.cpp:151-173 == Raisr_AVX256.cpp:366-391 */
 {
     const float ONEQTR_PI = (float)(M_PI / 4.0);
@@ -109,41 +111,115 @@ static float atan2_approx(float y, float x)     /* Raisr_AVX512.cpp:151-173 == R
     return (y < 0.0f) ? -1.0f * v : v;
 }
 
-/* wide16 != 0: GetHashValue_AVX512_32f_16Elements; == 0: GetHashValue_AVX256_32f_8Elements, which the
- * AVX512 build runs on the 8-wide tail blocks of every row (Raisr.cpp:1133-1134, 1247-1250). */
-static int hash_bucket(const float g[3], const oracle_pass_params *p, int wide16)
+/* Bucket index from angle / strength / coherence.  wide16: thresholds <= value, NaN -> 0 (Raisr_AVX512.cpp:242-249);
+ * 8-wide: 2 - [value <= Q0] - [value <= Q1], NaN -> 2 (Raisr_AVX256.cpp:457-464). */
+static int quantise(float ang_scaled, float str, float coh, const oracle_pass_params *p, int wide16)
 {
-    sqrt_fn SQ = p->sqrt_mode == ORACLE_SQRT_X86 ? (wide16 ? sqrt_x86_14 : sqrt_x86_ps) : sqrt_ieee;
-    const float a = g[0], b = g[1], d = g[2];
-    float T = a + d;
-    float ad = a * d, bb = b * b;
-    float D = ad - bb;
-    float s = SQ((T * T) / 4.0f - D);
-    float hT = T / 2.0f;
-    float L1 = hT + s, L2 = hT - s;
-    float x = (b != 0.0f) ? (L1 - d) : 1.0f;
-    float ang = atan2_approx(b, x);
-    ang = ang + ((ang < 0.0f) ? kPI : 0.0f);
-    float s1 = SQ(L1), s2 = SQ(L2);
-    float coh = (s1 - s2) / ((s1 + s2) + 0.00000000000000001f);
-    float str = L1;
-
-    const float qangle = 24.0f / kPI;                   /* gQAngle = gQuantizationAngle / PI, Raisr.cpp:1553 */
-    float fa = floorf(ang * qangle);
+    float fa = floorf(ang_scaled);
     int ai;
     if (!(fa >= -2147483648.0f && fa < 2147483648.0f)) ai = (int)0x80000000; /* cvtps_epi32 of NaN/overflow */
     else ai = (int)fa;
     if (ai < 0) ai = 0;
     if (ai > 23) ai = 23;
     int si, ci;
-    if (wide16) {   /* thresholds <= value; NaN compares false -> 0  (Raisr_AVX512.cpp:242-249) */
+    if (wide16) {
         si = (p->qstr[0] <= str) + (p->qstr[1] <= str);
         ci = (p->qcoh[0] <= coh) + (p->qcoh[1] <= coh);
-    } else {        /* 2 - [value <= Q0] - [value <= Q1]; NaN -> 2     (Raisr_AVX256.cpp:457-464) */
+    } else {
         si = 2 - ((str <= p->qstr[0]) + (str <= p->qstr[1]));
         ci = 2 - ((coh <= p->qcoh[0]) + (coh <= p->qcoh[1]));
     }
     return ai * 9 + si * 3 + ci;
+}
+
+/* ORACLE_SQRT_IEEE: the source semantics with IEEE sqrt and division.
+ * wide16 != 0: GetHashValue_AVX512_32f_16Elements; == 0: GetHashValue_AVX256_32f_8Elements, which the
+ * AVX512 build runs on the 8-wide tail blocks of every row (Raisr.cpp:1133-1134, 1247-1250). */
+static int hash_bucket_ieee(const float g[3], const oracle_pass_params *p, int wide16)
+{
+    const float a = g[0], b = g[1], d = g[2];
+    float T = a + d;
+    float ad = a * d, bb = b * b;
+    float D = ad - bb;
+    float s = sqrtf((T * T) / 4.0f - D);
+    float hT = T / 2.0f;
+    float L1 = hT + s, L2 = hT - s;
+    float x = (b != 0.0f) ? (L1 - d) : 1.0f;
+    float ang = atan2_approx(b, x);
+    ang = ang + ((ang < 0.0f) ? kPI : 0.0f);
+    float s1 = sqrtf(L1), s2 = sqrtf(L2);
+    float coh = (s1 - s2) / ((s1 + s2) + 0.00000000000000001f);
+    const float qangle = 24.0f / kPI;                   /* gQAngle = gQuantizationAngle / PI, Raisr.cpp:1553 */
+    return quantise(ang * qangle, L1, coh, p, wide16);
+}
+
+/* ORACLE_SQRT_X86: the same two functions AS COMPILED by g++ 13.3 with the reference's flag set
+ * (-O3 -ffast-math -march=native with AVX-512; CMakeLists.txt:23-41), transcribed from the disassembly of
+ * oracle/_ref/libraisr_ref.so (GetHashValue_AVX512_32f_16Elements at .text+0xa8e0; the 8-wide AVX2 variant
+ * inlined into processSegment).  What -ffast-math did:
+ *   - D and T*T/4 - D are contracted:  nD = fma(b,b,-(a*d));  z = fma(T*T, 0.25, nD)        (16-wide)
+ *                                       z = (T*T)*NR(rcpps(4)) + nD  (two roundings)           (8-wide)
+ *   - every division is reciprocal-approximation + one Newton step:  n/den = n * ((r+r) - r*(r*den)), r = rcp(den)
+ *     (16-wide: vrcp14ps; 8-wide: vrcpps), EXCEPT the masked (x<0) atan2 branch of the 8-wide code, a true vdivps
+ *   - T/2 is T*0.5 (exact) in the 16-wide code but T * NR(rcpps(2)) in the 8-wide code
+ *   - gQAngle = 24 * (1/PI) (reciprocal constant), one ulp below 24/PI
+ *   - sqrt is rcp(rsqrt(x)) as written in the source (Raisr_AVX512.cpp:200,221-222; Raisr_AVX256.cpp:419,441-442). */
+static float nr_recip(float r, float den) { float e = r * (r * den); return (r + r) - e; }
+
+static float atan_poly(float q, float base, float b)
+{
+    float v = fmaf(fmaf(q, 0.1963f * q, -0.9817f), q, base);
+    return (b < 0.0f) ? -v : v;
+}
+
+static int hash_bucket_x86(const float g[3], const oracle_pass_params *p, int wide16)
+{
+    const float a = g[0], b = g[1], d = g[2];
+    const float ONEQTR_PI = (float)(M_PI / 4.0), THRQTR_PI = (float)(3.0 * M_PI / 4.0);
+    const float qangle = 24.0f * (1.0f / kPI);
+    float T = a + d;
+    float nD = fmaf(b, b, -(a * d));
+    float ay = fabsf(b) + 1e-10f;
+    float L1, L2, q, s1, s2, coh;
+    if (wide16) {
+        float z = fmaf(T * T, 0.25f, nD);
+        float s = oracle_x86_rcp14(oracle_x86_rsqrt14(z));
+        L1 = fmaf(T, 0.5f, s);
+        L2 = fmaf(T, 0.5f, -s);
+        float x = (b != 0.0f) ? (L1 - d) : 1.0f;
+        float pl = x + ay, mn = x - ay, nd = ay - x;
+        q = (x < 0.0f) ? pl * nr_recip(oracle_x86_rcp14(nd), nd) : mn * nr_recip(oracle_x86_rcp14(pl), pl);
+        float ang = atan_poly(q, (x < 0.0f) ? THRQTR_PI : ONEQTR_PI, b);
+        ang = ang + ((ang < 0.0f) ? kPI : 0.0f);
+        s1 = oracle_x86_rcp14(oracle_x86_rsqrt14(L1));
+        s2 = oracle_x86_rcp14(oracle_x86_rsqrt14(L2));
+        float den = (s1 + s2) + 0.00000000000000001f;
+        coh = (s1 - s2) * nr_recip(oracle_x86_rcp14(den), den);
+        return quantise(ang * qangle, L1, coh, p, 1);
+    } else {
+        float quarter = nr_recip(oracle_x86_rcpps(4.0f), 4.0f);
+        float half = nr_recip(oracle_x86_rcpps(2.0f), 2.0f);
+        float z = (T * T) * quarter + nD;
+        float s = oracle_x86_rcpps(oracle_x86_rsqrtps(z));
+        float hT = T * half;
+        L1 = s + hT;
+        L2 = hT - s;
+        float x = (b != 0.0f) ? (L1 - d) : 1.0f;
+        float pl = x + ay, mn = x - ay, nd = ay - x;
+        q = (x < 0.0f) ? pl / nd : mn * nr_recip(oracle_x86_rcpps(pl), pl);
+        float ang = atan_poly(q, (x < 0.0f) ? THRQTR_PI : ONEQTR_PI, b);
+        ang = ang + ((ang < 0.0f) ? kPI : 0.0f);
+        s1 = oracle_x86_rcpps(oracle_x86_rsqrtps(L1));
+        s2 = oracle_x86_rcpps(oracle_x86_rsqrtps(L2));
+        float den = (s1 + s2) + 0.00000000000000001f;
+        coh = (s1 - s2) * nr_recip(oracle_x86_rcpps(den), den);
+        return quantise(ang * qangle, L1, coh, p, 0);
+    }
+}
+
+static int hash_bucket(const float g[3], const oracle_pass_params *p, int wide16)
+{
+    return p->sqrt_mode == ORACLE_SQRT_X86 ? hash_bucket_x86(g, p, wide16) : hash_bucket_ieee(g, p, wide16);
 }
 
 /* ---- 121-tap filter, DotProdPatch_AVX512_32f (Raisr_AVX512.cpp:134-149) ---------------------- */
@@ -178,7 +254,7 @@ void oracle_hashed_cols(int W, int *c_end, int *tail_start)
 }
 
 /* ---- census blend, CTCountOfBitsChangedSegment_AVX256_32f (Raisr_AVX256.cpp:68-166) ----------- */
-static uint16_t blend_pixel(const float *L, const float *Hh, int W, int r, int c, int lo, int hi)
+static uint16_t blend_pixel(const float *L, const float *Hh, int W, int r, int c, int lo, int hi, int x86)
 {
     const float lc = L[(size_t)r * W + c], hc = Hh[(size_t)r * W + c];
     int ham = 0;
@@ -191,9 +267,10 @@ static uint16_t blend_pixel(const float *L, const float *Hh, int W, int r, int c
         }
     float w = (float)ham / 8.0f;
     float w2 = 1.0f - w;
-    /* w*lc is exact (k/8 times an integer < 2^16), so mul+mul+add and any FMA contraction of it agree
-     * unless (1-w)*hc is contracted; tests/test_oracle_vs_ref.py pins which one the compiled reference does. */
-    float v = (w * lc + w2 * hc) + 0.5f;
+    /* Source semantics (ORACLE_SQRT_IEEE): w*LR + (1-w)*HR, then + 0.5, each rounded.  As compiled with -ffast-math
+     * (ORACLE_SQRT_X86; vector body and scalar tail alike, see the vfmadd132 pair before vrndscaleps in the reference
+     * binary): fma(1-w, HR, fma(LR, w, 0.5)) -- w*LR + 0.5 is exact, so the whole sum is rounded once. */
+    float v = x86 ? fmaf(w2, hc, fmaf(lc, w, 0.5f)) : (w * lc + w2 * hc) + 0.5f;
     float fv = floorf(v);
     int iv = (int)fv;
     if (iv > hi) iv = hi;
@@ -250,7 +327,7 @@ int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
      * (row/edge memcpys, Raisr.cpp:999-1028, 1252-1265) */
     for (size_t i = 0; i < N; i++) out[i] = S[i];
     for (int r = 1; r < H - 1; r++)
-        for (int c = 1; c < W - 1; c++) out[(size_t)r * W + c] = blend_pixel(L, Hh, W, r, c, p->lo, p->hi);
+        for (int c = 1; c < W - 1; c++) out[(size_t)r * W + c] = blend_pixel(L, Hh, W, r, c, p->lo, p->hi, p->sqrt_mode == ORACLE_SQRT_X86);
     free(L); free(Hh);
     return 0;
 }

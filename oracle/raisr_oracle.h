@@ -31,8 +31,10 @@ extern "C" {
 
 enum {
     ORACLE_SQRT_IEEE = 0,   /* the spec: IEEE sqrtf and '/'                                  */
-    ORACLE_SQRT_X86  = 1    /* pinning aid: sqrt := vrcp14(vrsqrt14(x)) (16-wide hash) and
-                               rcpps(rsqrtps(x)) (8-wide tail hash), executed on the host CPU */
+    ORACLE_SQRT_X86  = 1    /* the hash AS COMPILED (g++ 13.3, the reference's -O3 -ffast-math flag set):
+                               vrcp14(vrsqrt14(x)) / rcpps(rsqrtps(x)) square roots, reciprocal+Newton
+                               divisions, contracted determinant -- executed with the real instructions
+                               on the host CPU; bit-identical to oracle/_ref/libraisr_ref*.so */
 };
 
 typedef struct {

@@ -262,3 +262,55 @@ def run_handler(L, folder, inY, ratio=2.0, bits=8, rng=VideoRange, threads=1, as
     finally:
         L.RNLHandler_Deinit()
     return outY.copy(), outU, outV
+
+
+def run_ref_subprocess(folder_name, inY, ratio=2.0, bits=8, rng=VideoRange, threads=1, asm=AVX512, passes=1, mode=1,
+                       want_hash=False):
+    """Runs the compiled reference in a FRESH process (its configuration lives in process globals that RNLInit does not
+    reset, Raisr_globals.h:140-203).  Returns (outY, hash planes or None)."""
+    import pickle
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "in.npy"), inY)
+        code = (
+            "import sys, pickle, ctypes as C, numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "import raisr_testlib as T\n"
+            "a = pickle.load(open(%r, 'rb'))\n"
+            "img = np.load(%r)\n"
+            "L = T.handler_lib(T.ref_lib_path(dbg=a['want_hash']))\n"
+            "H, W = img.shape; oW, oH = int(W * a['ratio']), int(H * a['ratio'])\n"
+            "planes = []\n"
+            "if a['want_hash']:\n"
+            "    hp = (C.c_void_p * 2).in_dll(L, 'g_raisr_dbg_hash')\n"
+            "    for i in range(a['passes']):\n"
+            "        lr = a['passes'] == 2 and a['mode'] == 2 and i == 0\n"
+            "        planes.append(np.full((H, W) if lr else (oH, oW), -1, np.int32)); hp[i] = planes[-1].ctypes.data\n"
+            "out = T.run_handler(L, T.filter_folder(a['folder']), img, a['ratio'], a['bits'], a['rng'], a['threads'], a['asm'], a['passes'], a['mode'])\n"
+            "np.savez(%r, out_y=out[0], **{'hash%%d' %% i: p for i, p in enumerate(planes)})\n"
+        ) % (os.path.dirname(os.path.abspath(__file__)), os.path.join(td, "args.pkl"), os.path.join(td, "in.npy"),
+             os.path.join(td, "out.npz"))
+        pickle.dump(dict(folder=folder_name, ratio=ratio, bits=bits, rng=rng, threads=threads, asm=asm, passes=passes,
+                         mode=mode, want_hash=want_hash), open(os.path.join(td, "args.pkl"), "wb"))
+        subprocess.check_call([sys.executable, "-c", code], stdout=subprocess.DEVNULL)
+        z = np.load(os.path.join(td, "out.npz"))
+        hashes = [z["hash%d" % i] for i in range(passes)] if want_hash else None
+        return z["out_y"], hashes
+
+
+def load_golden(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    ratio, bits, passes, mode, rng, seed = z["meta"]
+    return dict(in_y=z["in_y"], in_u=z["in_u"], in_v=z["in_v"], out_y=z["out_y"], out_u=z["out_u"], out_v=z["out_v"],
+                hash=[z["hash%d" % i].astype(np.int32) for i in range(int(passes))], ratio=float(ratio), bits=int(bits),
+                passes=int(passes), mode=int(mode), rng=int(rng), folder=str(z["folder"]), kind=str(z["kind"]))
+
+
+def golden_names():
+    d = os.path.join(ROOT, "tests", "golden")
+    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz"))
+
+
+def have_avx512():
+    return "avx512f" in open("/proc/cpuinfo").read()

@@ -102,3 +102,86 @@ def test_constant_frame_invariants():
     out, _ = run_engine(f, img, want_hash=False)
     assert (out[0, :] == 7).all() and (out[-1, :] == 7).all() and (out[:, 0] == 7).all() and (out[:, -1] == 7).all()
     assert (out[1:6, 1:-1] == 16).all()
+
+
+# ---- x86-exact numerics: the CUDA engine against the COMPILED REFERENCE ---------------------------------------
+@pytest.mark.parametrize("name", T.golden_names())
+def test_x86_mode_bit_identical_to_reference_golden(name):
+    """RAISR_NUMERICS_X86 vs tests/golden (outputs of the untouched reference sources built with their own flags):
+    bit-identical buckets, Y and chroma."""
+    g = T.load_golden(name)
+    h, w = g["in_y"].shape
+    oW, oH = int(w * g["ratio"]), int(h * g["ratio"])
+    eng = B.Engine(T.filter_folder(g["folder"]), g["ratio"], g["bits"], g["rng"], g["passes"], g["mode"],
+                   numerics=B.NUMERICS_X86, keep_hash=True)
+    eng.set_res(w, h, oW, oH, g["in_u"].shape[1], g["in_u"].shape[0], g["out_u"].shape[1], g["out_u"].shape[0])
+    oy, ou, ov = np.zeros_like(g["out_y"]), np.zeros_like(g["out_u"]), np.zeros_like(g["out_v"])
+    assert eng.process_host(g["in_y"], oy, g["in_u"], g["in_v"], ou, ov) == 0
+    for i in range(g["passes"]):
+        hv = eng.read_hash(i, g["hash"][i].shape[1], g["hash"][i].shape[0])
+        assert np.array_equal(hv, g["hash"][i]), "pass %d buckets: %d differ" % (i, (hv != g["hash"][i]).sum())
+    eng.close()
+    assert np.array_equal(oy, g["out_y"]), "Y differs on %d px" % (oy != g["out_y"]).sum()
+    assert np.array_equal(ou, g["out_u"]) and np.array_equal(ov, g["out_v"])
+
+
+@pytest.mark.skipif(not T.have_avx512(), reason="ORACLE_SQRT_X86 executes vrcp14ps/vrsqrt14ps on the host")
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size,kind", [
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (960, 540), "mix"),          # BASELINE configs[0]: 540p -> 1080p
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1, (480, 270), "noise"),
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (480, 270), "edges"),
+    ("filters_1.5x/filters_highres", 1.5, 8, 1, 1, (640, 360), "mix"),
+])
+def test_x86_mode_vs_oracle_x86(folder, ratio, bits, passes, mode, size, kind):
+    """Larger frames: CUDA x86 mode vs the oracle's as-compiled hash (itself pinned to the reference binary)."""
+    w, h = size
+    f = T.filter_folder(folder)
+    img = T.synth_frame(w, h, bits, seed=99 + w, kind=kind)
+    out, hashes = run_engine(f, img, ratio, bits, passes, mode, numerics=B.NUMERICS_X86)
+    m1, m2 = oracle_models(f, bits, passes, sqrt_mode=1)
+    ref, h1, h2 = T.oracle_process_y(img, int(w * ratio), int(h * ratio), m1, m2, passes, mode, want_hash=True)
+    assert np.array_equal(hashes[0], h1), "pass-1 buckets differ: %d" % (hashes[0] != h1).sum()
+    if passes == 2:
+        assert np.array_equal(hashes[1], h2), "pass-2 buckets differ: %d" % (hashes[1] != h2).sum()
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.skipif(not (T.have_ref() and T.have_avx512()), reason="oracle/_ref not usable on this host")
+def test_x86_mode_vs_live_reference_1080p():
+    """configs[0] against the reference library run live on this host's CPU (AVX512 path, 1 thread)."""
+    img = T.synth_frame(960, 540, 8, seed=2024)
+    ref_y, _ = T.run_ref_subprocess("filters_2x/filters_lowres", img)
+    out, _ = run_engine(T.filter_folder("filters_2x/filters_lowres"), img, numerics=B.NUMERICS_X86, want_hash=False)
+    assert np.array_equal(out, ref_y), "Y differs on %d px" % (out != ref_y).sum()
+
+
+def test_full_size_properties_4k():
+    """BASELINE configs[1] size (1080p -> 4K), size-independent properties instead of a full oracle run:
+    (1) row-band launches reproduce the full-frame launch bit for bit (band independence, SURVEY 8(a11));
+    (2) device entry point == host entry point; (3) 1-px frame equals the cheap upscale; (4) range clamp holds inside."""
+    import torch
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = T.synth_frame(1920, 1080, 8, seed=7)
+    eng = B.Engine(f, 2.0, 8, T.VideoRange, 1, 1, numerics=B.NUMERICS_AUTO)
+    eng.set_res(1920, 1080, 3840, 2160)
+    full = np.zeros((2160, 3840), np.uint8)
+    assert eng.process_host(img, full) == 0
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.zeros((2160, 3840), dtype=torch.uint8, device="cuda")
+    bands = [(0, 540), (540, 1082), (1082, 2160)]
+    for r0, r1 in bands:
+        assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0), d_out.data_ptr(), d_out.stride(0), r0, r1) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), full)
+    up = T.oracle_resize(img, 3840, 2160)
+    assert np.array_equal(full[0], up[0]) and np.array_equal(full[-1], up[-1])
+    assert np.array_equal(full[:, 0], up[:, 0]) and np.array_equal(full[:, -1], up[:, -1])
+    inner = full[1:-1, 1:-1]
+    assert inner.min() >= 16 and inner.max() <= 235
+    # a 256-row slab checked against the oracle (rows far from the slab do not influence it)
+    m = T.OracleModel(f, 8, sqrt_mode=1 if T.have_avx512() else 0)
+    if T.have_avx512():
+        slab_in = img[400:400 + 160]                      # LR rows 400..559 -> HR rows 800..1119
+        ref = T.oracle_process_y(slab_in, 3840, 320, m)
+        assert np.array_equal(full[800 + 16:1120 - 16], ref[16:-16])
+    eng.close()

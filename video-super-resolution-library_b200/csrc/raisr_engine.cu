@@ -126,6 +126,7 @@ struct raisr_cuda_engine {
     int in_w = 0, in_h = 0, out_w = 0, out_h = 0, in_cw = 0, in_ch = 0, out_cw = 0, out_ch = 0;
     AxisMap yx, yy, cx, cy;
     int up_src_h = 0;
+    float quarter = 0.25f, half = 0.5f;
     Plane d_in[3], d_out[3], d_mid;
     int *d_hash[2] = {nullptr, nullptr};
     int hash_w[2] = {0, 0}, hash_h[2] = {0, 0};
@@ -225,7 +226,15 @@ void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
     p->lo = e->lo; p->hi = e->hi;
     hashed_cols(W, &p->c_end, &p->tail_start, &p->ov_end);
     p->numerics = e->cfg.numerics;
-    p->qangle = (float)e->model.q_angle / 3.141592653f;      // gQAngle = gQuantizationAngle / PI (Raisr.cpp:1553)
+    if (e->cfg.numerics == RAISR_NUMERICS_X86) {
+        // as compiled: gQAngle = angles * (1/PI); the 8-wide hash divides by 4 and 2 through rcpps + one Newton step
+        const float rpi = 1.0f / 3.141592653f;
+        p->qangle = (float)e->model.q_angle * rpi;
+        p->quarter = e->quarter;
+        p->half = e->half;
+    } else {
+        p->qangle = (float)e->model.q_angle / 3.141592653f;  // gQAngle = gQuantizationAngle / PI (Raisr.cpp:1553)
+    }
     p->nangles = e->model.q_angle;
     p->hash_out = e->d_hash[pass_idx];
     p->blending = 2;
@@ -310,11 +319,6 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         std::cout << "[RAISR ERROR] bit depth: " << cfg->bit_depth << "bits is NOT supported." << std::endl;
         return RNLErrorBadParameter;
     }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        std::cout << "[RAISR ERROR] no CUDA device: the B200 engine has no CPU path" << std::endl;
-        return RNLErrorUndefined;
-    }
     raisr_cuda_engine *e = new raisr_cuda_engine;
     e->cfg = *cfg;
     e->cfg.passes = passes;
@@ -329,6 +333,12 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
 
     int rc = load_model(e->model_path, cfg->ratio, cfg->bit_depth, passes, &e->model);
     if (rc != RNLErrorNone) { delete e; return rc; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        std::cout << "[RAISR ERROR] no CUDA device: the B200 engine has no CPU path" << std::endl;
+        delete e;
+        return RNLErrorUndefined;
+    }
 
     auto fail = [&](int code) { raisr_cuda_destroy(e); return code; };
     if (cfg->device >= 0) {
@@ -368,6 +378,11 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (e->cfg.numerics == RAISR_NUMERICS_X86) {
         const uint16_t *src[4]; size_t n[4];
         x86_tables(src, n);
+        if (src[3]) {
+            auto nr = [](float r, float den) { const float t = r * den; const float e2 = r * t; return (r + r) - e2; };
+            e->quarter = nr(x86_rcp<11, 11, false>(src[3], 4.0f), 4.0f);
+            e->half = nr(x86_rcp<11, 11, false>(src[3], 2.0f), 2.0f);
+        }
         for (int i = 0; i < 4; ++i) {
             if (!src[i]) {
                 std::cout << "[RAISR ERROR] x86 numerics tables are not built into this library" << std::endl;

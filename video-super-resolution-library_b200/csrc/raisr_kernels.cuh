@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace raisr {
 
@@ -48,8 +49,9 @@ struct PassParams {
     int tail_start;          // columns >= tail_start are hashed by the 8-wide variant (Raisr.cpp:1246-1250)
     int ov_end;              // columns in [tail_start, ov_end) are hashed by BOTH variants, 8-wide last
     int numerics;            // RAISR_NUMERICS_*
-    float qangle;            // angle bins / PI
+    float qangle;            // angle bins / PI (IEEE) or angle bins * (1/PI) (X86)
     int nangles;
+    float quarter, half;     // X86 8-wide hash constants
     int *hash_out;           // optional [H][W] bucket plane (parity tests), -1 = not hashed
     int blending;            // 2 = CountOfBitsChanged
     const uint16_t *lut_rsqrt14, *lut_rcp14, *lut_rsqrtps, *lut_rcpps;   // x86 numerics tables (may be null)
@@ -121,103 +123,155 @@ __device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool 
 }
 
 // ---- x86 approximation instructions via tables (numerics == X86) ------------------------------------
-// vrsqrt14ps / vrcp14ps / rsqrtps / rcpps restricted to positive normal inputs, plus the special values the
-// hash can produce (0, negative, NaN).  Tables: see csrc/x86_tables.h for the layout.
-__device__ __forceinline__ float lut_rsqrt(const uint16_t *t, int idx_bits, float x)
+// vrsqrt14ps / vrcp14ps / rsqrtps / rcpps reproduced bit for bit (tables: tools/gen_x86_tables.py, verified there
+// against the real instructions for every mantissa).  All four scale exactly with the exponent; the value depends on
+// the top IDX mantissa bits (and the exponent's parity for the square roots); the 14-bit forms return an exact power
+// of two for a zero mantissa.  Table entry v encodes the result for [1,2) (or [1,4)) as 0x3f000000 + (v << SHIFT).
+template <int IDX, int SHIFT, bool EXACT_POW2>
+__host__ __device__ __forceinline__ float x86_rsqrt(const uint16_t *t, float x)
 {
-    if (!(x >= 0.0f)) return __int_as_float(0x7fc00000) * ((x != x) ? 1.0f : -1.0f);   // NaN (x86 returns -NaN for negatives; sign of NaN never matters here)
-    if (x == 0.0f) return __int_as_float(0x7f800000);
-    if (x == __int_as_float(0x7f800000)) return 0.0f;
+#ifdef __CUDA_ARCH__
     const unsigned u = __float_as_uint(x);
-    const int e = (int)(u >> 23) - 127;                 // unbiased exponent
-    const unsigned par = e & 1;                          // odd exponent -> second half of the table
-    const unsigned idx = (par << idx_bits) | ((u & 0x7fffffu) >> (23 - idx_bits));
-    const unsigned ent = t[idx];                         // top 16 bits of the result's mantissa field for exponent slot below
-    // result = 2^(-(e - par)/2) * r, r in (0.5, 1] for par = 0 -> [1/sqrt2 ...]; the table stores the full
-    // 16 significant mantissa bits plus one bit telling whether the result's exponent is one lower.
-    const int half = (e - (int)par) / 2;                 // exact: e - par is even (floor for negatives handled by parity)
-    const unsigned man = (ent & 0x7fffu) << 8;           // 15 stored fraction bits -> mantissa bits 22..8
-    const int eadj = (ent >> 15) ? -1 : 0;               // result in [0.5,1) * 2^-half  vs exactly 1.0 * 2^-half
-    const int re = 127 - half + eadj;
-    return __uint_as_float(((unsigned)re << 23) | man);
+#else
+    unsigned u; memcpy(&u, &x, 4);
+#endif
+    unsigned r;
+    if (u == 0u) r = 0x7f800000u;                                  // +0 -> +inf
+    else if (u == 0x80000000u) r = 0xff800000u;                    // -0 -> -inf
+    else if (u > 0x7f800000u) r = 0x7fc00000u;                     // negative or NaN -> NaN
+    else if (u == 0x7f800000u) r = 0u;                             // +inf -> 0
+    else {
+        const int E = (int)(u >> 23) - 127;
+        const unsigned m = u & 0x7fffffu;
+        const int par = E & 1;
+        const int k = (E - par) >> 1;                              // x = [1,4) * 4^k
+        if (EXACT_POW2 && par == 0 && m == 0) r = (unsigned)(127 - k) << 23;
+        else r = 0x3f000000u + ((unsigned)t[((unsigned)par << IDX) | (m >> (23 - IDX))] << SHIFT) - ((unsigned)k << 23);
+    }
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(r);
+#else
+    float f; memcpy(&f, &r, 4); return f;
+#endif
 }
 
-__device__ __forceinline__ float lut_rcp(const uint16_t *t, int idx_bits, float x)
+template <int IDX, int SHIFT, bool EXACT_POW2>
+__host__ __device__ __forceinline__ float x86_rcp(const uint16_t *t, float x)
 {
-    if (x != x) return x;
+#ifdef __CUDA_ARCH__
     const unsigned u = __float_as_uint(x);
-    const unsigned sign = u & 0x80000000u;
-    const unsigned au = u & 0x7fffffffu;
-    if (au == 0) return __uint_as_float(sign | 0x7f800000u);
-    if (au == 0x7f800000u) return __uint_as_float(sign);
-    const int e = (int)(au >> 23) - 127;
-    const unsigned idx = (au & 0x7fffffu) >> (23 - idx_bits);
-    const unsigned ent = t[idx];
-    const unsigned man = (ent & 0x7fffu) << 8;
-    const int eadj = (ent >> 15) ? -1 : 0;               // 1/m for m in (1,2) lies in (0.5,1): exponent -1; m == 1 -> 1.0
-    const int re = 127 - e + eadj;
-    if (re <= 0) return __uint_as_float(sign);           // would be denormal: never reached by the hash's value range
-    return __uint_as_float(sign | ((unsigned)re << 23) | man);
+#else
+    unsigned u; memcpy(&u, &x, 4);
+#endif
+    const unsigned sign = u & 0x80000000u, au = u & 0x7fffffffu;
+    unsigned r;
+    if (au > 0x7f800000u) r = u;                                   // NaN
+    else if (au == 0u) r = sign | 0x7f800000u;
+    else if (au == 0x7f800000u) r = sign;
+    else {
+        const int E = (int)(au >> 23) - 127;
+        const unsigned m = au & 0x7fffffu;
+        if (EXACT_POW2 && m == 0) r = sign | ((unsigned)(127 - E) << 23);
+        else r = sign | (0x3f000000u + ((unsigned)t[m >> (23 - IDX)] << SHIFT) - ((unsigned)E << 23));
+    }
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(r);
+#else
+    float f; memcpy(&f, &r, 4); return f;
+#endif
 }
 
 struct HashCtx {
     float qstr0, qstr1, qcoh0, qcoh1;
     int numerics;
-    float qangle;
+    float qangle;            // IEEE: angles / PI;  X86: angles * (1 / PI)   (what g++ -ffast-math emits for Raisr.cpp:1553)
     int nangles;
+    float quarter, half;     // X86 8-wide hash: Newton-refined rcpps(4), rcpps(2)
     const uint16_t *rsqrt14, *rcp14, *rsqrtps, *rcpps;
 };
 
-template <bool WIDE16>
-__device__ __forceinline__ float hash_sqrt(const HashCtx &h, float x)
-{
-    if (h.numerics == 0) return __fsqrt_rn(x);
-    if (WIDE16) return lut_rcp(h.rcp14, 16, lut_rsqrt(h.rsqrt14, 15, x));     // Raisr_AVX512.cpp:200,221-222
-    return lut_rcp(h.rcpps, 12, lut_rsqrt(h.rsqrtps, 12, x));                 // Raisr_AVX256.cpp:419,441-442
-}
-
-// atan2 approximation, Raisr_AVX512.cpp:151-173 (== Raisr_AVX256.cpp:366-391)
-__device__ __forceinline__ float atan2_approx(float y, float x)
+// atan2 approximation, Raisr_AVX512.cpp:151-173 (== Raisr_AVX256.cpp:366-391), given the quotient q
+__device__ __forceinline__ float atan_poly(float q, bool xneg, float b)
 {
     const float ONEQTR_PI = 0.78539816339744830962f, THRQTR_PI = 2.35619449019234492885f;
-    const float ay = fadd(fabsf(y), 1e-10f);
-    const bool neg = x < 0.0f;
-    const float num = neg ? fadd(x, ay) : fsub(x, ay);
-    const float den = neg ? fsub(ay, x) : fadd(x, ay);
-    const float q = __fdiv_rn(num, den);
-    const float base = neg ? THRQTR_PI : ONEQTR_PI;
-    const float v = ffma(ffma(fmul(0.1963f, q), q, -0.9817f), q, base);
-    return (y < 0.0f) ? fmul(-1.0f, v) : v;
+    const float v = ffma(ffma(fmul(0.1963f, q), q, -0.9817f), q, xneg ? THRQTR_PI : ONEQTR_PI);
+    return (b < 0.0f) ? -v : v;
 }
+
+__device__ __forceinline__ int quantise(const HashCtx &h, bool wide16, float ang, float str, float coh)
+{
+    ang = fadd(ang, (ang < 0.0f) ? 3.141592653f : 0.0f);                       // PI, Raisr_globals.h:29
+    const float fa = floorf(fmul(ang, h.qangle));
+    const int ai = (fa >= 0.0f) ? ((fa < (float)h.nangles) ? (int)fa : h.nangles - 1) : 0;   // NaN -> INT_MIN -> max(.,0) = 0
+    int si, ci;
+    if (wide16) {            // thresholds <= value, NaN -> 0   (Raisr_AVX512.cpp:242-249)
+        si = (h.qstr0 <= str) + (h.qstr1 <= str);
+        ci = (h.qcoh0 <= coh) + (h.qcoh1 <= coh);
+    } else {                 // 2 - [value <= Q0] - [value <= Q1], NaN -> 2   (Raisr_AVX256.cpp:457-464)
+        si = 2 - ((str <= h.qstr0) + (str <= h.qstr1));
+        ci = 2 - ((coh <= h.qcoh0) + (coh <= h.qcoh1));
+    }
+    return ai * 9 + si * 3 + ci;
+}
+
+// reciprocal approximation + one Newton step, the form g++ -ffast-math gives every division of the hash
+__device__ __forceinline__ float nr_recip(float r, float den) { return fsub(fadd(r, r), fmul(r, fmul(r, den))); }
 
 // Bucket of one pixel from its structure tensor (a, b, d).
 // WIDE16: GetHashValue_AVX512_32f_16Elements (Raisr_AVX512.cpp:175-258); else the 8-wide AVX2 variant the
 // AVX-512 build runs on row tails (Raisr_AVX256.cpp:393-472; Raisr.cpp:1133-1134).
+// numerics IEEE: the source semantics with sqrt.rn / div.rn (oracle: hash_bucket_ieee).
+// numerics X86 : the functions as compiled by g++ 13.3 -O3 -ffast-math (oracle: hash_bucket_x86, transcribed from the
+//                disassembly of the reference binary): contracted determinant, rcp(rsqrt()) roots, rcp+Newton divisions.
 template <bool WIDE16>
 __device__ __forceinline__ int hash_bucket(const HashCtx &h, float a, float b, float d)
 {
-    const float PI_F = 3.141592653f;                             // Raisr_globals.h:29
     const float T = fadd(a, d);
-    const float D = fsub(fmul(a, d), fmul(b, b));
-    const float s = hash_sqrt<WIDE16>(h, fsub(fmul(fmul(T, T), 0.25f), D));
-    const float hT = fmul(T, 0.5f);
-    const float L1 = fadd(hT, s), L2 = fsub(hT, s);
-    const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
-    float ang = atan2_approx(b, x);
-    ang = fadd(ang, (ang < 0.0f) ? PI_F : 0.0f);
-    const float s1 = hash_sqrt<WIDE16>(h, L1), s2 = hash_sqrt<WIDE16>(h, L2);
-    const float coh = __fdiv_rn(fsub(s1, s2), fadd(fadd(s1, s2), 0.00000000000000001f));
-    const float fa = floorf(fmul(ang, h.qangle));
-    const int ai = (fa >= 0.0f) ? ((fa < (float)h.nangles) ? (int)fa : h.nangles - 1) : 0;   // NaN -> INT_MIN -> max(.,0) = 0
-    int si, ci;
-    if (WIDE16) {
-        si = (h.qstr0 <= L1) + (h.qstr1 <= L1);
-        ci = (h.qcoh0 <= coh) + (h.qcoh1 <= coh);
-    } else {
-        si = 2 - ((L1 <= h.qstr0) + (L1 <= h.qstr1));
-        ci = 2 - ((coh <= h.qcoh0) + (coh <= h.qcoh1));
+    const float ay = fadd(fabsf(b), 1e-10f);
+    if (h.numerics == 0) {
+        const float D = fsub(fmul(a, d), fmul(b, b));
+        const float s = __fsqrt_rn(fsub(fmul(fmul(T, T), 0.25f), D));
+        const float hT = fmul(T, 0.5f);
+        const float L1 = fadd(hT, s), L2 = fsub(hT, s);
+        const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
+        const bool neg = x < 0.0f;
+        const float q = __fdiv_rn(neg ? fadd(x, ay) : fsub(x, ay), neg ? fsub(ay, x) : fadd(x, ay));
+        const float s1 = __fsqrt_rn(L1), s2 = __fsqrt_rn(L2);
+        const float coh = __fdiv_rn(fsub(s1, s2), fadd(fadd(s1, s2), 0.00000000000000001f));
+        return quantise(h, WIDE16, atan_poly(q, neg, b), L1, coh);
     }
-    return ai * 9 + si * 3 + ci;
+    const float nD = ffma(b, b, -fmul(a, d));
+    float L1, L2, q, s1, s2, rden;
+    bool neg;
+    if (WIDE16) {
+        const float z = ffma(fmul(T, T), 0.25f, nD);
+        const float s = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, z));
+        L1 = ffma(T, 0.5f, s);
+        L2 = ffma(T, 0.5f, -s);
+        const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
+        neg = x < 0.0f;
+        const float den = neg ? fsub(ay, x) : fadd(x, ay);
+        q = fmul(neg ? fadd(x, ay) : fsub(x, ay), nr_recip(x86_rcp<16, 7, true>(h.rcp14, den), den));
+        s1 = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, L1));
+        s2 = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, L2));
+        const float cden = fadd(fadd(s1, s2), 0.00000000000000001f);
+        rden = nr_recip(x86_rcp<16, 7, true>(h.rcp14, cden), cden);
+    } else {
+        const float z = fadd(fmul(fmul(T, T), h.quarter), nD);
+        const float s = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, z));
+        const float hT = fmul(T, h.half);
+        L1 = fadd(s, hT);
+        L2 = fsub(hT, s);
+        const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
+        neg = x < 0.0f;
+        const float pl = fadd(x, ay);
+        q = neg ? __fdiv_rn(pl, fsub(ay, x)) : fmul(fsub(x, ay), nr_recip(x86_rcp<11, 11, false>(h.rcpps, pl), pl));
+        s1 = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, L1));
+        s2 = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, L2));
+        const float cden = fadd(fadd(s1, s2), 0.00000000000000001f);
+        rden = nr_recip(x86_rcp<11, 11, false>(h.rcpps, cden), cden);
+    }
+    return quantise(h, WIDE16, atan_poly(q, neg, b), L1, fmul(fsub(s1, s2), rden));
 }
 
 // 11 lane values -> the reference's 16-lane tree (Raisr_AVX512.cpp:37-44).  Pixel A of a pair occupies
@@ -265,6 +319,20 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// The reference's 16 -> 1 lane tree (sumitup_ps_512, Raisr_AVX512.cpp:37-44) over the 8 lanes of a pixel, lane q holding
+// chains 2q (a0) and 2q+1 (a1):  t8[j] = acc[j] + acc[j+8];  t4[j] = t8[j] + t8[j+4];  t2[j] = t4[j] + t4[j+2];  t2[0] + t2[1].
+// Butterfly form: 4 shuffles instead of 6; every add has the same two operands as the reference's (fp add commutes).
+__device__ __forceinline__ float tree8(float a0, float a1, int q)
+{
+    const bool hi = q >= 4;
+    // lanes 0..3 end up with t8[2q] = a0[q] + a0[q+4], lanes 4..7 with t8[2(q-4)+1] = a1[q-4] + a1[q]
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 4, 8);
+    float v = fadd(hi ? a1 : a0, recv);
+    v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 2, 8));       // t4[0] lanes 0,2 | t4[2] lanes 1,3 | t4[1] lanes 4,6 | t4[3] lanes 5,7
+    v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 1, 8));       // t2[0] lanes 0..3 | t2[1] lanes 4..7
+    return fadd(v, __shfl_xor_sync(0xffffffffu, v, 4, 8));
+}
+
 // 121-tap filter in the reference's order -- 16 lane chains over 8 chunks of 16 taps, then the 16-lane tree
 // (DotProdPatch_AVX512_32f, Raisr_AVX512.cpp:134-149) -- evaluated by 8 GPU lanes per pixel: lane q owns chains 2q
 // and 2q+1.  frow = the pixel's filter row in the slice buffer, stored lane-permuted as [n][q][4] =
@@ -285,14 +353,7 @@ __device__ __forceinline__ float dot8(const float *sp, const float *frow, const 
         a0 = ffma(p2, f.z, a0);
         a1 = ffma(p3, f.w, a1);
     }
-    // tree: t8[j] = acc[j] + acc[j+8] (lane q <- q+4); t4[j] = t8[j] + t8[j+4] (q <- q+2); t2[j] = t4[j] + t4[j+2] (q <- q+1)
-    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 4, 8));
-    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 4, 8));
-    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 2, 8));
-    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 2, 8));
-    a0 = fadd(a0, __shfl_down_sync(0xffffffffu, a0, 1, 8));
-    a1 = fadd(a1, __shfl_down_sync(0xffffffffu, a1, 1, 8));
-    return fadd(a0, a1);          // valid in lane q == 0
+    return tree8(a0, a1, q);          // same value in the pixel's 8 lanes
 }
 
 // UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),
@@ -368,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     }
     __syncthreads();
 
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.lut_rsqrt14, p.lut_rcp14, p.lut_rsqrtps, p.lut_rcpps};
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, p.lut_rsqrt14, p.lut_rcp14, p.lut_rsqrtps, p.lut_rcpps};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 
     for (int h0 = 0; h0 < hh; h0 += RB) {
@@ -506,12 +567,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    // tree: t8[j] = acc[j]+acc[j+8] (lane q <- q+4); t4[j] = t8[j]+t8[j+4] (q <- q+2); t2[j] = t4[j]+t4[j+2] (q <- q+1)
-                    float x = a0[u], y = a1[u];
-                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 4, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 4, 8));
-                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 2, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 2, 8));
-                    x = fadd(x, __shfl_down_sync(0xffffffffu, x, 1, 8)); y = fadd(y, __shfl_down_sync(0xffffffffu, y, 1, 8));
-                    const float cur = fadd(x, y);                 // valid in lane q == 0
+                    const float cur = tree8(a0[u], a1[u], q);     // identical in all 8 lanes of the pixel
                     bool ok = (cur > flo) && (cur < fhi);         // strict range test, Raisr.cpp:1192-1196
                     float res = cur;
                     const int j = jb + 4 * JS * u;
@@ -558,7 +614,9 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
                 }
             const float w = fmul((float)ham, 0.125f);
-            const float v = fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f);
+            // source semantics: (w*LR + (1-w)*HR) + 0.5; as compiled (-ffast-math): fma(1-w, HR, fma(LR, w, 0.5)), one rounding
+            const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
+                                              : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
             int r = min(max((int)floorf(v), p.lo), p.hi);
             if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;   // 1-px frame: the integer upscale itself (Raisr.cpp:999-1028,1252-1265)
             iv[e] = r;
