@@ -327,7 +327,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "sharding": "frame-parallel, no collective",
                        "l2": "rotating %d distinct frame sets (%.0f MB > 126 MB L2)" % (NBUF, NBUF * BYTES_FRAME / 1e6),
-                       "numerics": "x86-exact" if eng.cfg.numerics == 1 else "auto"},
+                       "numerics": "x86-exact (bit-identical to the compiled reference)" if eng.numerics() == 1 else "ieee"},
             "e2e": {"value": e2e, "unit": "frames/s",
                     "h2d_bytes_per_step": FRAMES_PER_STEP * (IN_W * IN_H + 2 * (IN_W // 2) * (IN_H // 2)),
                     "d2h_bytes_per_step": FRAMES_PER_STEP * (OUT_W * OUT_H + 2 * (OUT_W // 2) * (OUT_H // 2))},

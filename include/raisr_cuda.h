@@ -72,6 +72,9 @@ int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_
  * w*h entries with w,h the plane that pass ran on.  Needs cfg.keep_hash. */
 int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count);
 
+/* RAISR_NUMERICS_* actually in effect (resolves RAISR_NUMERICS_X86_IF_AVAILABLE) */
+int raisr_cuda_numerics(const raisr_cuda_engine *e);
+
 /* number of kernels the engine launched since creation (bench's gpu_launches) */
 unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e);
 

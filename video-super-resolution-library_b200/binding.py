@@ -40,6 +40,8 @@ def lib():
         L.raisr_cuda_read_hash.argtypes = [vp, C.c_int, vp, sz]
         L.raisr_cuda_launch_count.restype = C.c_ulonglong
         L.raisr_cuda_launch_count.argtypes = [vp]
+        L.raisr_cuda_numerics.restype = C.c_int
+        L.raisr_cuda_numerics.argtypes = [vp]
         L.raisr_cuda_destroy.restype = None
         L.raisr_cuda_destroy.argtypes = [vp]
         L.raisr_cuda_version.restype = C.c_char_p
@@ -90,6 +92,9 @@ class Engine:
         if rc != 0:
             raise RuntimeError("raisr_cuda_read_hash failed: 0x%08x" % (rc & 0xffffffff))
         return out
+
+    def numerics(self):
+        return int(self.L.raisr_cuda_numerics(self.h))
 
     def launch_count(self):
         return int(self.L.raisr_cuda_launch_count(self.h))

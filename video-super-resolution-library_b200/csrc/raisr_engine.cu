@@ -120,7 +120,7 @@ struct raisr_cuda_engine {
     int device = 0;
     int num_sms = 148;
     float *d_filters[2] = {nullptr, nullptr};
-    uint16_t *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
     // geometry
     bool have_res = false;
     int in_w = 0, in_h = 0, out_w = 0, out_h = 0, in_cw = 0, in_ch = 0, out_cw = 0, out_ch = 0;
@@ -238,7 +238,8 @@ void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
     p->nangles = e->model.q_angle;
     p->hash_out = e->d_hash[pass_idx];
     p->blending = 2;
-    p->lut_rsqrt14 = e->d_lut[0]; p->lut_rcp14 = e->d_lut[1]; p->lut_rsqrtps = e->d_lut[2]; p->lut_rcpps = e->d_lut[3];
+    p->lut_rsqrt14 = static_cast<const uint2 *>(e->d_lut[0]); p->lut_rcp14 = static_cast<const uint2 *>(e->d_lut[1]);
+    p->lut_rsqrtps = static_cast<const uint16_t *>(e->d_lut[2]); p->lut_rcpps = static_cast<const uint16_t *>(e->d_lut[3]);
 }
 
 void set_upscale(const raisr_cuda_engine *e, PassParams *p)
@@ -370,28 +371,25 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
             cudaMemcpy(e->d_filters[i], dev.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(RNLErrorInsufficientResources);
     }
-    if (e->cfg.numerics == RAISR_NUMERICS_X86_IF_AVAILABLE) {
-        const uint16_t *src[4]; size_t n[4];
-        x86_tables(src, n);
-        e->cfg.numerics = (src[0] && src[1] && src[2] && src[3]) ? RAISR_NUMERICS_X86 : RAISR_NUMERICS_IEEE;
-    }
+    X86Tables xt{};
+    const bool have_tables = x86_tables(&xt);
+    if (e->cfg.numerics == RAISR_NUMERICS_X86_IF_AVAILABLE) e->cfg.numerics = have_tables ? RAISR_NUMERICS_X86 : RAISR_NUMERICS_IEEE;
     if (e->cfg.numerics == RAISR_NUMERICS_X86) {
-        const uint16_t *src[4]; size_t n[4];
-        x86_tables(src, n);
-        if (src[3]) {
-            auto nr = [](float r, float den) { const float t = r * den; const float e2 = r * t; return (r + r) - e2; };
-            e->quarter = nr(x86_rcp<11, 11, false>(src[3], 4.0f), 4.0f);
-            e->half = nr(x86_rcp<11, 11, false>(src[3], 2.0f), 2.0f);
+        if (!have_tables) {
+            std::cout << "[RAISR ERROR] x86 numerics tables are not built into this library" << std::endl;
+            return fail(RNLErrorBadParameter);
         }
-        for (int i = 0; i < 4; ++i) {
-            if (!src[i]) {
-                std::cout << "[RAISR ERROR] x86 numerics tables are not built into this library" << std::endl;
-                return fail(RNLErrorBadParameter);
-            }
-            if (cudaMalloc(&e->d_lut[i], n[i] * sizeof(uint16_t)) != cudaSuccess ||
-                cudaMemcpy(e->d_lut[i], src[i], n[i] * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        // the 8-wide hash as compiled divides by 4 and by 2 through rcpps + one Newton step
+        auto nr = [](float r, float den) { const float t = r * den; const float e2 = r * t; return (r + r) - e2; };
+        e->quarter = nr(x86_rcpps(xt.rcpps, 4.0f), 4.0f);
+        e->half = nr(x86_rcpps(xt.rcpps, 2.0f), 2.0f);
+        const void *src[4] = {xt.rsqrt14, xt.rcp14, xt.rsqrtps, xt.rcpps};
+        const size_t bytes[4] = {kRsqrt14Words * sizeof(uint32_t), kRcp14Words * sizeof(uint32_t), kRsqrtpsEntries * sizeof(uint16_t),
+                                 kRcppsEntries * sizeof(uint16_t)};
+        for (int i = 0; i < 4; ++i)
+            if (cudaMalloc(&e->d_lut[i], bytes[i]) != cudaSuccess ||
+                cudaMemcpy(e->d_lut[i], src[i], bytes[i], cudaMemcpyHostToDevice) != cudaSuccess)
                 return fail(RNLErrorInsufficientResources);
-        }
     }
     if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -515,6 +513,8 @@ int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size
 }
 
 unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e) { return e ? e->launches : 0; }
+
+int raisr_cuda_numerics(const raisr_cuda_engine *e) { return e ? e->cfg.numerics : -1; }
 
 void raisr_cuda_destroy(raisr_cuda_engine *e)
 {

@@ -54,7 +54,8 @@ struct PassParams {
     float quarter, half;     // X86 8-wide hash constants
     int *hash_out;           // optional [H][W] bucket plane (parity tests), -1 = not hashed
     int blending;            // 2 = CountOfBitsChanged
-    const uint16_t *lut_rsqrt14, *lut_rcp14, *lut_rsqrtps, *lut_rcpps;   // x86 numerics tables (may be null)
+    const uint2 *lut_rsqrt14, *lut_rcp14;      // x86 numerics: (c0,c1) runs of the 14-bit instructions, 128 entries each (may be null)
+    const uint16_t *lut_rsqrtps, *lut_rcpps;   // x86 numerics: SSE approximation tables, 2048 entries each (may be null)
 };
 
 // Gaussian weights, folded: c_gw[i][m] = w[i][m] = w[i][10-m], m = 0..5   (Raisr_globals.h:208-264)
@@ -83,7 +84,8 @@ constexpr size_t OFF_HR = OFF_S + sizeof(float) * SH * SP;
 constexpr size_t OFF_F = (OFF_HR + sizeof(float) * HH * HP + 127) & ~(size_t)127;
 constexpr size_t OFF_HASH = OFF_F + sizeof(float) * SLICE_FLOATS;
 constexpr size_t OFF_HASH2 = OFF_HASH + (size_t)HH * HP;
-constexpr size_t OFF_MBAR = (OFF_HASH2 + (size_t)HH * OVW + 15) & ~(size_t)15;
+constexpr size_t OFF_LUT = (OFF_HASH2 + (size_t)HH * OVW + 15) & ~(size_t)15;    // 256 x uint2: rsqrt14 runs, rcp14 runs
+constexpr size_t OFF_MBAR = OFF_LUT + 256 * sizeof(uint2);
 constexpr size_t SMEM_BYTES = OFF_MBAR + 16;
 static_assert(QW == 128 && HH % RB == 0 && SP >= SW && TW % 4 == 0 && HP % 4 == 0, "tile geometry");
 constexpr int LRW = SW / 2 + 1, LRP = LRW + 1;   // low-res tile of the 2x fast path (lives in the slice buffer during stage A)
@@ -124,61 +126,84 @@ __device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool 
 
 // ---- x86 approximation instructions via tables (numerics == X86) ------------------------------------
 // vrsqrt14ps / vrcp14ps / rsqrtps / rcpps reproduced bit for bit (tables: tools/gen_x86_tables.py, verified there
-// against the real instructions for every mantissa).  All four scale exactly with the exponent; the value depends on
-// the top IDX mantissa bits (and the exponent's parity for the square roots); the 14-bit forms return an exact power
-// of two for a zero mantissa.  Table entry v encodes the result for [1,2) (or [1,4)) as 0x3f000000 + (v << SHIFT).
-template <int IDX, int SHIFT, bool EXACT_POW2>
-__host__ __device__ __forceinline__ float x86_rsqrt(const uint16_t *t, float x)
+// against the real instructions for every mantissa).  All four scale exactly with the exponent and depend on the top
+// mantissa bits only (plus the exponent's parity for the square roots).  A table value v encodes the result for an
+// argument in [1,2) (or [1,4)) as 0x3f000000 + (v << SHIFT).
+//   14-bit forms: v = (c0 - c1 * low9) >> 9 with (c0, c1) selected by the top 7 (rcp) / parity + top 6 (rsqrt) bits;
+//                 a zero mantissa returns an exact power of two.
+//   SSE forms   : v = table[top 11 (rcp) / parity + top 10 (rsqrt) bits].
+__host__ __device__ __forceinline__ unsigned f2u(float x)
 {
 #ifdef __CUDA_ARCH__
-    const unsigned u = __float_as_uint(x);
+    return __float_as_uint(x);
 #else
-    unsigned u; memcpy(&u, &x, 4);
+    unsigned u; memcpy(&u, &x, 4); return u;
 #endif
-    unsigned r;
-    if (u == 0u) r = 0x7f800000u;                                  // +0 -> +inf
-    else if (u == 0x80000000u) r = 0xff800000u;                    // -0 -> -inf
-    else if (u > 0x7f800000u) r = 0x7fc00000u;                     // negative or NaN -> NaN
-    else if (u == 0x7f800000u) r = 0u;                             // +inf -> 0
-    else {
-        const int E = (int)(u >> 23) - 127;
-        const unsigned m = u & 0x7fffffu;
-        const int par = E & 1;
-        const int k = (E - par) >> 1;                              // x = [1,4) * 4^k
-        if (EXACT_POW2 && par == 0 && m == 0) r = (unsigned)(127 - k) << 23;
-        else r = 0x3f000000u + ((unsigned)t[((unsigned)par << IDX) | (m >> (23 - IDX))] << SHIFT) - ((unsigned)k << 23);
-    }
+}
+__host__ __device__ __forceinline__ float u2f(unsigned u)
+{
 #ifdef __CUDA_ARCH__
-    return __uint_as_float(r);
+    return __uint_as_float(u);
 #else
-    float f; memcpy(&f, &r, 4); return f;
+    float f; memcpy(&f, &u, 4); return f;
 #endif
 }
 
-template <int IDX, int SHIFT, bool EXACT_POW2>
-__host__ __device__ __forceinline__ float x86_rcp(const uint16_t *t, float x)
+__host__ __device__ __forceinline__ float x86_rsqrt14(const uint2 *t, float x)
 {
-#ifdef __CUDA_ARCH__
-    const unsigned u = __float_as_uint(x);
-#else
-    unsigned u; memcpy(&u, &x, 4);
-#endif
+    const unsigned u = f2u(x);
+    if (u == 0u) return u2f(0x7f800000u);                          // +0 -> +inf
+    if (u == 0x80000000u) return u2f(0xff800000u);                 // -0 -> -inf
+    if (u > 0x7f800000u) return u2f(0x7fc00000u);                  // negative or NaN -> NaN
+    if (u == 0x7f800000u) return 0.0f;                             // +inf -> 0
+    const int E = (int)(u >> 23) - 127;
+    const unsigned m = u & 0x7fffffu;
+    const int par = E & 1;
+    const int k = (E - par) >> 1;                                  // x = [1,4) * 4^k
+    if (par == 0 && m == 0) return u2f((unsigned)(127 - k) << 23);
+    const uint2 c = t[(par << 6) | (m >> 17)];
+    const unsigned v = (c.x - c.y * ((m >> 8) & 0x1ffu)) >> 9;
+    return u2f(0x3f000000u + (v << 7) - ((unsigned)k << 23));
+}
+
+__host__ __device__ __forceinline__ float x86_rcp14(const uint2 *t, float x)
+{
+    const unsigned u = f2u(x);
     const unsigned sign = u & 0x80000000u, au = u & 0x7fffffffu;
-    unsigned r;
-    if (au > 0x7f800000u) r = u;                                   // NaN
-    else if (au == 0u) r = sign | 0x7f800000u;
-    else if (au == 0x7f800000u) r = sign;
-    else {
-        const int E = (int)(au >> 23) - 127;
-        const unsigned m = au & 0x7fffffu;
-        if (EXACT_POW2 && m == 0) r = sign | ((unsigned)(127 - E) << 23);
-        else r = sign | (0x3f000000u + ((unsigned)t[m >> (23 - IDX)] << SHIFT) - ((unsigned)E << 23));
-    }
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(r);
-#else
-    float f; memcpy(&f, &r, 4); return f;
-#endif
+    if (au > 0x7f800000u) return x;                                // NaN
+    if (au == 0u) return u2f(sign | 0x7f800000u);
+    if (au == 0x7f800000u) return u2f(sign);
+    const int E = (int)(au >> 23) - 127;
+    const unsigned m = au & 0x7fffffu;
+    if (m == 0) return u2f(sign | ((unsigned)(127 - E) << 23));
+    const uint2 c = t[m >> 16];
+    const unsigned v = (c.x - c.y * ((m >> 7) & 0x1ffu)) >> 9;
+    return u2f(sign | (0x3f000000u + (v << 7) - ((unsigned)E << 23)));
+}
+
+__host__ __device__ __forceinline__ float x86_rsqrtps(const uint16_t *t, float x)
+{
+    const unsigned u = f2u(x);
+    if (u == 0u) return u2f(0x7f800000u);
+    if (u == 0x80000000u) return u2f(0xff800000u);
+    if (u > 0x7f800000u) return u2f(0x7fc00000u);
+    if (u == 0x7f800000u) return 0.0f;
+    const int E = (int)(u >> 23) - 127;
+    const unsigned m = u & 0x7fffffu;
+    const int par = E & 1;
+    const int k = (E - par) >> 1;
+    return u2f(0x3f000000u + ((unsigned)t[(par << 10) | (m >> 13)] << 11) - ((unsigned)k << 23));
+}
+
+__host__ __device__ __forceinline__ float x86_rcpps(const uint16_t *t, float x)
+{
+    const unsigned u = f2u(x);
+    const unsigned sign = u & 0x80000000u, au = u & 0x7fffffffu;
+    if (au > 0x7f800000u) return x;
+    if (au == 0u) return u2f(sign | 0x7f800000u);
+    if (au == 0x7f800000u) return u2f(sign);
+    const int E = (int)(au >> 23) - 127;
+    return u2f(sign | (0x3f000000u + ((unsigned)t[(au & 0x7fffffu) >> 12] << 11) - ((unsigned)E << 23)));
 }
 
 struct HashCtx {
@@ -187,7 +212,8 @@ struct HashCtx {
     float qangle;            // IEEE: angles / PI;  X86: angles * (1 / PI)   (what g++ -ffast-math emits for Raisr.cpp:1553)
     int nangles;
     float quarter, half;     // X86 8-wide hash: Newton-refined rcpps(4), rcpps(2)
-    const uint16_t *rsqrt14, *rcp14, *rsqrtps, *rcpps;
+    const uint2 *rsqrt14, *rcp14;          // shared-memory copies of the 14-bit instruction tables
+    const uint16_t *rsqrtps, *rcpps;       // global (row tails only)
 };
 
 // atan2 approximation, Raisr_AVX512.cpp:151-173 (== Raisr_AVX256.cpp:366-391), given the quotient q
@@ -245,31 +271,31 @@ __device__ __forceinline__ int hash_bucket(const HashCtx &h, float a, float b, f
     bool neg;
     if (WIDE16) {
         const float z = ffma(fmul(T, T), 0.25f, nD);
-        const float s = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, z));
+        const float s = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, z));
         L1 = ffma(T, 0.5f, s);
         L2 = ffma(T, 0.5f, -s);
         const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
         neg = x < 0.0f;
         const float den = neg ? fsub(ay, x) : fadd(x, ay);
-        q = fmul(neg ? fadd(x, ay) : fsub(x, ay), nr_recip(x86_rcp<16, 7, true>(h.rcp14, den), den));
-        s1 = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, L1));
-        s2 = x86_rcp<16, 7, true>(h.rcp14, x86_rsqrt<15, 7, true>(h.rsqrt14, L2));
+        q = fmul(neg ? fadd(x, ay) : fsub(x, ay), nr_recip(x86_rcp14(h.rcp14, den), den));
+        s1 = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, L1));
+        s2 = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, L2));
         const float cden = fadd(fadd(s1, s2), 0.00000000000000001f);
-        rden = nr_recip(x86_rcp<16, 7, true>(h.rcp14, cden), cden);
+        rden = nr_recip(x86_rcp14(h.rcp14, cden), cden);
     } else {
         const float z = fadd(fmul(fmul(T, T), h.quarter), nD);
-        const float s = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, z));
+        const float s = x86_rcpps(h.rcpps, x86_rsqrtps(h.rsqrtps, z));
         const float hT = fmul(T, h.half);
         L1 = fadd(s, hT);
         L2 = fsub(hT, s);
         const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
         neg = x < 0.0f;
         const float pl = fadd(x, ay);
-        q = neg ? __fdiv_rn(pl, fsub(ay, x)) : fmul(fsub(x, ay), nr_recip(x86_rcp<11, 11, false>(h.rcpps, pl), pl));
-        s1 = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, L1));
-        s2 = x86_rcp<11, 11, false>(h.rcpps, x86_rsqrt<10, 11, false>(h.rsqrtps, L2));
+        q = neg ? __fdiv_rn(pl, fsub(ay, x)) : fmul(fsub(x, ay), nr_recip(x86_rcpps(h.rcpps, pl), pl));
+        s1 = x86_rcpps(h.rcpps, x86_rsqrtps(h.rsqrtps, L1));
+        s2 = x86_rcpps(h.rcpps, x86_rsqrtps(h.rsqrtps, L2));
         const float cden = fadd(fadd(s1, s2), 0.00000000000000001f);
-        rden = nr_recip(x86_rcp<11, 11, false>(h.rcpps, cden), cden);
+        rden = nr_recip(x86_rcpps(h.rcpps, cden), cden);
     }
     return quantise(h, WIDE16, atan_poly(q, neg, b), L1, fmul(fsub(s1, s2), rden));
 }
@@ -370,9 +396,11 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     float *sQ = sGY + GR * QW;                                    // [RB][18][QW]
     unsigned char *sHash = smem_raw + OFF_HASH;                   // [HH][HP] bucket, 255 = not hashed
     unsigned char *sHash2 = smem_raw + OFF_HASH2;                 // [HH][OVW] 16-wide bucket of overlap columns, 255 = same
+    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + OFF_LUT);  // [0,128) rsqrt14, [128,256) rcp14
     void *mbar = smem_raw + OFF_MBAR;
 
     const int tid = threadIdx.x;
+    if (p.numerics != 0 && tid < 256) sLut[tid] = (tid < 128) ? p.lut_rsqrt14[tid] : p.lut_rcp14[tid - 128];
     const int th = p.tile_h;
     const int x0 = blockIdx.x * TW;
     const int y0 = p.row0 + blockIdx.y * th;
@@ -429,7 +457,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     }
     __syncthreads();
 
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, p.lut_rsqrt14, p.lut_rcp14, p.lut_rsqrtps, p.lut_rcpps};
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 
     for (int h0 = 0; h0 < hh; h0 += RB) {

@@ -1,7 +1,9 @@
 #include "x86_tables.h"
 namespace raisr {
-__attribute__((weak)) void x86_tables(const uint16_t *src[4], size_t n[4])
+__attribute__((weak)) bool x86_tables(X86Tables *t)
 {
-    for (int i = 0; i < 4; ++i) { src[i] = nullptr; n[i] = 0; }
+    t->rsqrt14 = t->rcp14 = nullptr;
+    t->rsqrtps = t->rcpps = nullptr;
+    return false;
 }
-}
+}  // namespace raisr
