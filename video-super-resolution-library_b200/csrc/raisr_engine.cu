@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <numeric>
@@ -133,6 +134,13 @@ struct raisr_cuda_engine {
     cudaStream_t stream = nullptr, stream_uv = nullptr;
     cudaEvent_t ev_uv = nullptr, ev_in = nullptr;
     unsigned long long launches = 0;
+    // host-pointer pipeline: the final pass signals finished row bands, the D2H stream waits on the counters
+    static constexpr int kMaxBands = 8;
+    unsigned *d_band_done = nullptr;
+    cudaStream_t stream_d2h = nullptr;
+    typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+    WaitValue32Fn wait_value32 = nullptr;
+    int last_grid_y = 0, last_tile_h = 0;   // geometry of the most recent pass launch
 };
 
 namespace {
@@ -183,6 +191,8 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
     while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && 2 * (ny + 1) <= rows) ++ny;
     q.tile_h = std::min(TH_MAX, (((rows + ny - 1) / ny) + 1) & ~1);
     const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
+    e->last_grid_y = (int)grid.y; e->last_tile_h = q.tile_h;
+    if (q.band_done) q.band_tiles_y = ((int)grid.y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
     q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch) % (4 * sizeof(PixT))) == 0;
     // 2x fast path: exact factor 2 in both axes and even band origin
     const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
@@ -252,7 +262,7 @@ void set_upscale(const raisr_cuda_engine *e, PassParams *p)
 
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
-             cudaStream_t s)
+             cudaStream_t s, unsigned *band_done = nullptr)
 {
     const bool two = e->cfg.passes == 2;
     const bool mode2 = two && e->cfg.two_pass_mode == 2;
@@ -262,6 +272,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         p.out = out_y; p.out_pitch = out_step; p.W = e->out_w; p.H = e->out_h; p.row0 = row0; p.row1 = row1;
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
+        p.band_done = band_done;
         return launch_pass(e, p, s);
     }
     if (row0 != 0 || row1 != e->out_h) {
@@ -277,6 +288,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = 0; p2.row1 = p2.H;
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
+    p2.band_done = band_done;
     int rc = launch_pass(e, p1, s);
     if (rc) return rc;
     return launch_pass(e, p2, s);
@@ -392,6 +404,18 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
                 return fail(RNLErrorInsufficientResources);
     }
     if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
+    if (cudaMalloc(&e->d_band_done, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(RNLErrorInsufficientResources);
+    {
+        // cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            e->wait_value32 = reinterpret_cast<raisr_cuda_engine::WaitValue32Fn>(fn);
+        else
+            cudaGetLastError();
+    }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream_uv, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_uv, cudaEventDisableTiming) != cudaSuccess ||
@@ -493,11 +517,38 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         }
     }
     CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
-    int rc = raisr_cuda_process_device_rows(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, blending, 0,
-                                            e->out_h, e->stream);
-    if (rc) return rc;
-    CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_OK(cudaStreamSynchronize(e->stream));
+    for (unsigned i = 0; i < e->cfg.passes; ++i)
+        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
+    const bool pipelined = e->wait_value32 != nullptr && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
+    if (pipelined) {
+        // The final pass counts finished tiles per row band; the D2H stream waits on each counter and copies that band
+        // while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
+        CUDA_OK(cudaMemsetAsync(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands, e->stream));
+        CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
+        int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done);
+        if (rc) return rc;
+        CUDA_OK(cudaStreamWaitEvent(e->stream_d2h, e->ev_in, 0));      // counters are zeroed before anybody waits on them
+        const int gx = (e->out_w + TW - 1) / TW;
+        const int bty = (e->last_grid_y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
+        for (int b = 0, ty = 0; ty < e->last_grid_y; ++b, ty += bty) {
+            const int tiles_y = std::min(bty, e->last_grid_y - ty);
+            const int r0 = ty * e->last_tile_h, r1 = std::min(e->out_h, (ty + tiles_y) * e->last_tile_h);
+            if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), (unsigned)(tiles_y * gx), 0 /* GEQ */) != 0) {
+                std::cout << "[RAISR ERROR] cuStreamWaitValue32 failed" << std::endl;
+                return RNLErrorUndefined;
+            }
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(out_y) + (size_t)r0 * out_y_step, out_y_step,
+                                      static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
+                                      e->out_w * bps, r1 - r0, cudaMemcpyDeviceToHost, e->stream_d2h));
+        }
+        CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+    } else {
+        int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
+        if (rc) return rc;
+        CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+    }
     if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
     return RNLErrorNone;
 }
@@ -527,6 +578,8 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     e->d_mid.release();
     e->yx.release(); e->yy.release(); e->cx.release(); e->cy.release();
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream_d2h) cudaStreamDestroy(e->stream_d2h);
+    cudaFree(e->d_band_done);
     if (e->stream_uv) cudaStreamDestroy(e->stream_uv);
     if (e->ev_uv) cudaEventDestroy(e->ev_uv);
     if (e->ev_in) cudaEventDestroy(e->ev_in);

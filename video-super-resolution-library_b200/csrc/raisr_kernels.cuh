@@ -43,6 +43,8 @@ struct PassParams {
     int nbuckets;            // 216
     int tile_h;              // output rows per CTA tile, <= TH_MAX (even)
     int vec_store;           // output base and pitch allow 4-pixel vector stores
+    unsigned *band_done;     // optional: per row band, the number of finished tiles (host-side copy pipeline)
+    int band_tiles_y;        // tile rows per band
     float qstr0, qstr1, qcoh0, qcoh1;
     int lo, hi;              // colour range
     int c_end;               // hashed columns are [6, c_end)                  (Raisr.cpp:1065-1066)
@@ -149,36 +151,36 @@ __host__ __device__ __forceinline__ float u2f(unsigned u)
 #endif
 }
 
+// (written select-style: the special cases are rare but must not cost divergent branches)
 __host__ __device__ __forceinline__ float x86_rsqrt14(const uint2 *t, float x)
 {
     const unsigned u = f2u(x);
-    if (u == 0u) return u2f(0x7f800000u);                          // +0 -> +inf
-    if (u == 0x80000000u) return u2f(0xff800000u);                 // -0 -> -inf
-    if (u > 0x7f800000u) return u2f(0x7fc00000u);                  // negative or NaN -> NaN
-    if (u == 0x7f800000u) return 0.0f;                             // +inf -> 0
-    const int E = (int)(u >> 23) - 127;
-    const unsigned m = u & 0x7fffffu;
-    const int par = E & 1;
-    const int k = (E - par) >> 1;                                  // x = [1,4) * 4^k
-    if (par == 0 && m == 0) return u2f((unsigned)(127 - k) << 23);
+    const unsigned e8 = (u >> 23) & 0xffu, m = u & 0x7fffffu;
+    const unsigned par = (e8 & 1u) ^ 1u;                           // parity of the unbiased exponent (127 is odd)
+    const int k = ((int)e8 - 127 - (int)par) >> 1;                 // x = [1,4) * 4^k
     const uint2 c = t[(par << 6) | (m >> 17)];
     const unsigned v = (c.x - c.y * ((m >> 8) & 0x1ffu)) >> 9;
-    return u2f(0x3f000000u + (v << 7) - ((unsigned)k << 23));
+    unsigned r = 0x3f000000u + (v << 7) - ((unsigned)k << 23);
+    r = ((par | m) == 0u) ? ((unsigned)(127 - k) << 23) : r;       // exact power of 4 -> exact power of 2
+    r = (e8 == 0u) ? 0x7f800000u : r;                              // +0 (and denormals, never produced here) -> +inf
+    r = (u == 0x7f800000u) ? 0u : r;                               // +inf -> 0
+    r = (u > 0x7f800000u) ? 0x7fc00000u : r;                       // NaN or negative -> NaN
+    r = (u == 0x80000000u) ? 0xff800000u : r;                      // -0 -> -inf
+    return u2f(r);
 }
 
 __host__ __device__ __forceinline__ float x86_rcp14(const uint2 *t, float x)
 {
     const unsigned u = f2u(x);
     const unsigned sign = u & 0x80000000u, au = u & 0x7fffffffu;
-    if (au > 0x7f800000u) return x;                                // NaN
-    if (au == 0u) return u2f(sign | 0x7f800000u);
-    if (au == 0x7f800000u) return u2f(sign);
-    const int E = (int)(au >> 23) - 127;
-    const unsigned m = au & 0x7fffffu;
-    if (m == 0) return u2f(sign | ((unsigned)(127 - E) << 23));
+    const unsigned e8 = au >> 23, m = au & 0x7fffffu;
     const uint2 c = t[m >> 16];
     const unsigned v = (c.x - c.y * ((m >> 7) & 0x1ffu)) >> 9;
-    return u2f(sign | (0x3f000000u + (v << 7) - ((unsigned)E << 23)));
+    unsigned r = 0x7e800000u - (e8 << 23) + (v << 7);              // 0x3f000000 + (v << 7) - ((e8 - 127) << 23)
+    r = (m == 0u) ? (0x7f000000u - (e8 << 23)) : r;                // exact power of 2
+    r = (e8 == 0u) ? 0x7f800000u : r;                              // 0 -> inf
+    r = (e8 == 255u) ? (m ? au : 0u) : r;                          // inf -> 0, NaN -> NaN
+    return u2f(sign | r);
 }
 
 __host__ __device__ __forceinline__ float x86_rsqrtps(const uint16_t *t, float x)
@@ -300,23 +302,17 @@ __device__ __forceinline__ int hash_bucket(const HashCtx &h, float a, float b, f
     return quantise(h, WIDE16, atan_poly(q, neg, b), L1, fmul(fsub(s1, s2), rden));
 }
 
-// 11 lane values -> the reference's 16-lane tree (Raisr_AVX512.cpp:37-44).  Pixel A of a pair occupies
-// lanes 1..11, pixel B lanes 2..12 (Raisr_AVX512.cpp:107-114), hence two pairings.
-__device__ __forceinline__ float tree_sum_A(const float *k)
+// 11 lane values -> the reference's 16-lane tree (sumitup_ps_512, Raisr_AVX512.cpp:37-44).  Pixel A of a pair occupies
+// lanes 1..11 and pixel B lanes 2..12 (Raisr_AVX512.cpp:107-114).  With P = k7+k3, Q = (k0+k8)+k4, R = (k1+k9)+k5,
+// S = (k2+k10)+k6 the tree of A is t4 = [P,Q,R,S] -> (P+R)+(Q+S) and the tree of B is t4 = [S,P,Q,R] -> (S+Q)+(P+R):
+// the same additions with commuted operands, i.e. the same fp32 result -- one function serves both.
+__device__ __forceinline__ float tree_sum(const float *k)
 {
-    const float t40 = fadd(k[7], k[3]);
-    const float t41 = fadd(fadd(k[0], k[8]), k[4]);
-    const float t42 = fadd(fadd(k[1], k[9]), k[5]);
-    const float t43 = fadd(fadd(k[2], k[10]), k[6]);
-    return fadd(fadd(t40, t42), fadd(t41, t43));
-}
-__device__ __forceinline__ float tree_sum_B(const float *k)
-{
-    const float t40 = fadd(k[6], fadd(k[2], k[10]));
-    const float t41 = fadd(k[7], k[3]);
-    const float t42 = fadd(fadd(k[0], k[8]), k[4]);
-    const float t43 = fadd(fadd(k[1], k[9]), k[5]);
-    return fadd(fadd(t40, t42), fadd(t41, t43));
+    const float P = fadd(k[7], k[3]);
+    const float Q = fadd(fadd(k[0], k[8]), k[4]);
+    const float R = fadd(fadd(k[1], k[9]), k[5]);
+    const float S = fadd(fadd(k[2], k[10]), k[6]);
+    return fadd(fadd(P, R), fadd(Q, S));
 }
 
 // ---- mbarrier / bulk-copy primitives (sm_90+ PTX) ---------------------------------------------------
@@ -518,7 +514,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                         const int m = k < 6 ? k : 10 - k;
                         lane[k] = qs[(m * 3 + k3) * QW + k];
                     }
-                    g[k3] = (c & 1) ? tree_sum_B(lane) : tree_sum_A(lane);
+                    g[k3] = tree_sum(lane);
                 }
                 if (c < p.tail_start) {
                     hv = hash_bucket<true>(hc, g[0], g[1], g[2]);
@@ -657,6 +653,14 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (X + e < W) orow[e] = (PixT)iv[e];
+        }
+    }
+    // row-band completion signal: the host's D2H stream waits (cuStreamWaitValue32) for all tiles of a band
+    if (p.band_done) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.band_done + blockIdx.y / p.band_tiles_y, 1u);
         }
     }
 }
