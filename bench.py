@@ -283,6 +283,10 @@ def main():
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count() - launches0
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
 
     # ---- dominant kernel alone (roofline): luma pass launches, CUDA events on the launching stream -----------
     for _ in range(FRAMES_PER_STEP):
@@ -329,8 +333,8 @@ def main():
                        "l2": "rotating %d distinct frame sets (%.0f MB > 126 MB L2)" % (NBUF, NBUF * BYTES_FRAME / 1e6),
                        "numerics": "x86-exact (bit-identical to the compiled reference)" if eng.numerics() == 1 else "ieee"},
             "e2e": {"value": e2e, "unit": "frames/s",
-                    "h2d_bytes_per_step": FRAMES_PER_STEP * (IN_W * IN_H + 2 * (IN_W // 2) * (IN_H // 2)),
-                    "d2h_bytes_per_step": FRAMES_PER_STEP * (OUT_W * OUT_H + 2 * (OUT_W // 2) * (OUT_H // 2))},
+                    "h2d_bytes_per_step": world * FRAMES_PER_STEP * (IN_W * IN_H + 2 * (IN_W // 2) * (IN_H // 2)),
+                    "d2h_bytes_per_step": world * FRAMES_PER_STEP * (OUT_W * OUT_H + 2 * (OUT_W // 2) * (OUT_H // 2))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "raisr_pass_kernel<uint8_t>", "achieved": achieved, "peak": peak,

@@ -183,6 +183,37 @@ __host__ __device__ __forceinline__ float x86_rcp14(const uint2 *t, float x)
     return u2f(sign | r);
 }
 
+// Fast forms for the 16-wide hash (device hot path).  Same values as the general functions above on the inputs the
+// hash can produce:
+//   x86_sqrt14(z) = vrcp14ps(vrsqrt14ps(z)) for z = +0 (-> inf -> 0), z < 0 or NaN (-> NaN) and positive normal z;
+//   x86_rcp14_pos(d) = vrcp14ps(d) for positive normal d.  The hash only divides by sums that are >= 1e-17 or NaN, and
+//   whenever the divisor is NaN so is the dividend, hence the quotient is NaN whatever finite pattern this returns.
+__device__ __forceinline__ float x86_rcp14_pos(const uint2 *t, float x)
+{
+    const unsigned u = __float_as_uint(x);
+    const unsigned e8 = u >> 23, m = u & 0x7fffffu;
+    const uint2 c = t[(m >> 16) & 127u];
+    const unsigned v = (c.x - c.y * ((m >> 7) & 0x1ffu)) >> 9;
+    const unsigned r = (m == 0u) ? 0x7f000000u : (0x7e800000u + (v << 7));
+    return __uint_as_float(r - (e8 << 23));
+}
+
+__device__ __forceinline__ float x86_sqrt14(const uint2 *trsq, const uint2 *trcp, float z)
+{
+    // y = vrsqrt14ps(z) for positive normal z
+    const unsigned u = __float_as_uint(z);
+    const unsigned e8 = (u >> 23) & 0xffu, m = u & 0x7fffffu;
+    const unsigned par = (e8 & 1u) ^ 1u;
+    const int k = ((int)e8 - 127 - (int)par) >> 1;
+    const uint2 c = trsq[(par << 6) | (m >> 17)];
+    const unsigned v = (c.x - c.y * ((m >> 8) & 0x1ffu)) >> 9;
+    unsigned y = 0x3f000000u + (v << 7) - ((unsigned)k << 23);
+    y = ((par | m) == 0u) ? ((unsigned)(127 - k) << 23) : y;
+    float r = x86_rcp14_pos(trcp, __uint_as_float(y));          // y is a positive normal number
+    r = (z == 0.0f) ? 0.0f : r;                                  // rsqrt14(0) = inf, rcp14(inf) = 0
+    return (z >= 0.0f) ? r : __uint_as_float(0x7fc00000u);       // negative or NaN
+}
+
 __host__ __device__ __forceinline__ float x86_rsqrtps(const uint16_t *t, float x)
 {
     const unsigned u = f2u(x);
@@ -273,17 +304,17 @@ __device__ __forceinline__ int hash_bucket(const HashCtx &h, float a, float b, f
     bool neg;
     if (WIDE16) {
         const float z = ffma(fmul(T, T), 0.25f, nD);
-        const float s = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, z));
+        const float s = x86_sqrt14(h.rsqrt14, h.rcp14, z);
         L1 = ffma(T, 0.5f, s);
         L2 = ffma(T, 0.5f, -s);
         const float x = (b != 0.0f) ? fsub(L1, d) : 1.0f;
         neg = x < 0.0f;
         const float den = neg ? fsub(ay, x) : fadd(x, ay);
-        q = fmul(neg ? fadd(x, ay) : fsub(x, ay), nr_recip(x86_rcp14(h.rcp14, den), den));
-        s1 = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, L1));
-        s2 = x86_rcp14(h.rcp14, x86_rsqrt14(h.rsqrt14, L2));
+        q = fmul(neg ? fadd(x, ay) : fsub(x, ay), nr_recip(x86_rcp14_pos(h.rcp14, den), den));
+        s1 = x86_sqrt14(h.rsqrt14, h.rcp14, L1);
+        s2 = x86_sqrt14(h.rsqrt14, h.rcp14, L2);
         const float cden = fadd(fadd(s1, s2), 0.00000000000000001f);
-        rden = nr_recip(x86_rcp14(h.rcp14, cden), cden);
+        rden = nr_recip(x86_rcp14_pos(h.rcp14, cden), cden);
     } else {
         const float z = fadd(fmul(fmul(T, T), h.quarter), nD);
         const float s = x86_rcpps(h.rcpps, x86_rsqrtps(h.rsqrtps, z));
