@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <type_traits>
 
 namespace raisr {
 
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
         constexpr int U = 4;                                      // pixel groups per warp iteration (one group = 4 pixels x 8 lanes)
         constexpr int NCOLS = (HW + JS - 1) / JS;                 // upper bound of same-type columns in a tile row
         constexpr int NBLK = (NCOLS + 4 * U - 1) / (4 * U);       // warp iterations per row
+        constexpr int ULAST = (NCOLS - 4 * U * (NBLK - 1) + 3) / 4; // groups in the last block of a row
         const int lane = tid & 31, warp = tid >> 5;
         const int g = lane >> 3, q = lane & 7;
         int off[8][2];
@@ -597,21 +599,20 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
             const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
             const int nrows = (hh - hfirst + JS - 1) / JS;
             mbar_wait(mbar, (unsigned)(t & 1));
-            for (int it = warp; it < nrows * NBLK; it += NT / 32) {
-                const int ri = it / NBLK, bi = it - ri * NBLK;
-                const int h = hfirst + ri * JS;
-                const int jb = jfirst + (bi * 4 * U + g) * JS;    // column of this lane's pixel in group u = 0; group u is 4*JS*u further
+            // one warp iteration = UU groups of 4 pixels of one tile row; the last block of a row is shorter
+            auto block = [&](auto uu, const int h, const int jb) {
+                constexpr int UU = decltype(uu)::value;
                 const float *sp = sS + (h + 1) * SP + jb + 1;
                 const unsigned char *hp = sHash + h * HP + jb;
-                int hv[U];
+                int hv[UU];
 #pragma unroll
-                for (int u = 0; u < U; ++u) hv[u] = (jb + 4 * JS * u < HW) ? hp[4 * JS * u] : 255;
-                float a0[U], a1[U];
+                for (int u = 0; u < UU; ++u) hv[u] = (jb + 4 * JS * u < HW) ? hp[4 * JS * u] : 255;
+                float a0[UU], a1[UU];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) {
                     const float *q0 = sp + off[2 * n][0], *q1 = sp + off[2 * n][1], *q2 = sp + off[2 * n + 1][0], *q3 = sp + off[2 * n + 1][1];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                    for (int u = 0; u < UU; ++u) {
                         const float4 f = sF4[(hv[u] == 255 ? 0 : hv[u]) * 32 + n * 8];
                         const float p0 = q0[4 * JS * u], p1 = q1[4 * JS * u], p2 = q2[4 * JS * u], p3 = q3[4 * JS * u];
                         if (n == 0) { a0[u] = fmul(p0, f.x); a1[u] = fmul(p1, f.y); }
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < UU; ++u) {
                     const float cur = tree8(a0[u], a1[u], q);     // identical in all 8 lanes of the pixel
                     bool ok = (cur > flo) && (cur < fhi);         // strict range test, Raisr.cpp:1192-1196
                     float res = cur;
@@ -637,6 +638,13 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     }
                     if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
                 }
+            };
+            for (int it = warp; it < nrows * NBLK; it += NT / 32) {
+                const int ri = it / NBLK, bi = it - ri * NBLK;
+                const int h = hfirst + ri * JS;
+                const int jb = jfirst + (bi * 4 * U + g) * JS;    // column of this lane's pixel in group u = 0; group u is 4*JS*u further
+                if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
+                else block(std::integral_constant<int, ULAST>{}, h, jb);
             }
             __syncthreads();
         }
