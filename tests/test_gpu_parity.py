@@ -185,3 +185,13 @@ def test_full_size_properties_4k():
         ref = T.oracle_process_y(slab_in, 3840, 320, m)
         assert np.array_equal(full[800 + 16:1120 - 16], ref[16:-16])
     eng.close()
+
+
+def test_pipelined_kernel_variant_is_bit_identical(monkeypatch):
+    """RAISR_CUDA_KERNEL=pipe (persistent warp-specialised schedule) must give exactly the default kernel's output."""
+    f = T.filter_folder("filters_2x/filters_highres")
+    img = T.synth_frame(500, 300, 8, seed=31, kind="mix")
+    base, hb = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
+    monkeypatch.setenv("RAISR_CUDA_KERNEL", "pipe")
+    pipe, hp = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
+    assert np.array_equal(base, pipe) and all(np.array_equal(a, b) for a, b in zip(hb, hp))

@@ -21,6 +21,7 @@
 #include "raisr/RaisrDefaults.h"
 #include "raisr_cuda.h"
 #include "raisr_kernels.cuh"
+#include "raisr_pipe_kernel.cuh"
 #include "raisr_model.h"
 #include "x86_tables.h"
 
@@ -120,6 +121,7 @@ struct raisr_cuda_engine {
     int lo = 0, hi = 255;
     int device = 0;
     int num_sms = 148;
+    bool use_pipe = false;          // RAISR_CUDA_KERNEL=pipe selects the warp-specialised persistent kernel (measured: no faster)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
     // geometry
@@ -172,9 +174,16 @@ int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStre
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_pipe_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES));
         attr_done = true;
     }
-    raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
+    if (e->use_pipe) {
+        // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
+        const int ntiles = (int)(grid.x * grid.y);
+        raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NT, PIPE_SMEM_BYTES, s>>>(q);
+    } else {
+        raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
+    }
     CUDA_OK(cudaGetLastError());
     e->launches++;
     return 0;
@@ -362,6 +371,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     }
     if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
+    if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "pipe") == 0;
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
         // contiguous bytes per step: tap k = 16m + j  ->  position (m/2)*32 + (j/2)*4 + (m%2)*2 + (j%2)   (see dot8())

@@ -1,0 +1,384 @@
+// raisr_pipe_kernel.cuh -- persistent, warp-specialised form of the RAISR pass kernel.
+//
+// Same arithmetic as raisr_pass_kernel (raisr_kernels.cuh: stages A-E, bit-identical results); what changes is the
+// schedule.  The profile of the phase-sequential kernel shows two kinds of stages: B/C (structure tensor + bucket) are
+// bound by FP32/ALU issue with the shared-memory pipe idle, D (121-tap filter out of the shared filter slice) is bound
+// by the shared-memory pipe with the FMA pipe idle.  Here one CTA per SM loops over tiles with two warp groups:
+//   producer warps : tile i+1 -- stream the upscaled rows through a 16-row ring, column chains, buckets  -> bucket tile[(i+1)&1]
+//   consumer warps : tile i   -- S tile, per-type filter slices (cp.async.bulk), 8-lane filter, blend, store
+// so the FMA-bound and the LSU-bound work of neighbouring tiles overlap on the same SM.  The hand-off is a pair of
+// mbarrier-guarded bucket tiles (full/empty), group-local synchronisation uses named barriers.
+//
+// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite) but NOT faster on B200 (0.85 ms vs 0.84 ms per
+// 4K frame with 8+8 warps, 0.98 ms with 4+12): with 128 registers x 512 threads the register file caps the CTA at 16
+// warps, and halving the warps of the filter stage halves the loads it keeps in flight -- it turns from shared-memory
+// bandwidth bound into latency bound and loses what the overlap gains.  Kept selectable (RAISR_CUDA_KERNEL=pipe) as the
+// measured alternative; the default is the phase-sequential kernel.
+#pragma once
+#include "raisr_kernels.cuh"
+
+namespace raisr {
+
+constexpr int NPW = 8;                       // producer warps
+constexpr int NCW = NT / 32 - NPW;           // consumer warps
+constexpr int NPT = NPW * 32, NCT = NCW * 32;
+constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
+constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
+static_assert(RBP * QW == NPT && RING >= RBP + 12 && (RING & (RING - 1)) == 0, "producer geometry");
+
+constexpr size_t POFF_S = 0;
+constexpr size_t POFF_HR = POFF_S + sizeof(float) * SH * SP;
+constexpr size_t POFF_F = (POFF_HR + sizeof(float) * HH * HP + 127) & ~(size_t)127;
+constexpr size_t POFF_HASH = POFF_F + sizeof(float) * SLICE_FLOATS;        // 2 bucket tiles
+constexpr size_t POFF_HASH2 = POFF_HASH + 2 * (size_t)HH * HP;             // 2 overlap-column tiles
+constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)HH * OVW + 15) & ~(size_t)15;
+constexpr size_t POFF_RING = POFF_LUT + 256 * sizeof(uint2);
+constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;
+constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * RBP * 18 * QW;       // slice, full[2], empty[2]
+constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 5 * 8;
+static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One sample of the upscaled plane for the producer's ring (out-of-frame coordinates are clamped: such samples only
+// feed pixels that are never hashed).
+template <typename PixT, int UPS>
+__device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
+{
+    if (UPS == 1) {
+        // exact 2x: even outputs weigh low-res (j-1, j) by (1,3), odd outputs (j, j+1) by (3,1); replicate border
+        const int jy = Y >> 1, jx = X >> 1;
+        const int ya = min(max((Y & 1) ? jy : jy - 1, 0), p.up_src_h - 1), yb = min(max((Y & 1) ? jy + 1 : jy, 0), p.up_src_h - 1);
+        const int xa = min(max((X & 1) ? jx : jx - 1, 0), p.in_w - 1), xb = min(max((X & 1) ? jx + 1 : jx, 0), p.in_w - 1);
+        const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
+        const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
+        const float a = (float)ra[xa], b = (float)ra[xb], c = (float)rb[xa], d = (float)rb[xb];
+        const float wya = (Y & 1) ? 3.0f : 1.0f, wyb = 4.0f - wya, wxa = (X & 1) ? 3.0f : 1.0f, wxb = 4.0f - wxa;
+        const float va = ffma(wya, a, fmul(wyb, c)), vb = ffma(wya, b, fmul(wyb, d));      // exact integers < 2^24
+        return floorf(fmul(fadd(ffma(wxa, va, fmul(wxb, vb)), 8.0f), 0.0625f));
+    }
+    const int Yc = min(max(Y, 0), p.H - 1), Xc = min(max(X, 0), p.W - 1);
+    return load_S<PixT>(p, Yc, Xc, UPS != 0);
+}
+
+template <typename PixT, int PT, int UPS>
+__global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sS = reinterpret_cast<float *>(smem_raw + POFF_S);
+    float *sHR = reinterpret_cast<float *>(smem_raw + POFF_HR);
+    float *sF = reinterpret_cast<float *>(smem_raw + POFF_F);
+    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
+    float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
+    float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
+    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
+    unsigned long long *mslice = mbars, *mfull0 = mbars + 1, *mempty0 = mbars + 3;
+
+    const int tid = threadIdx.x;
+    const int th = p.tile_h, hh = th + 2;
+    const int W = p.W, H = p.H;
+    const int gx = (W + TW - 1) / TW;
+    const int ntiles = gx * ((p.row1 - p.row0 + th - 1) / th);
+
+    if (p.numerics != 0 && tid < 256) sLut[tid] = (tid < 128) ? p.lut_rsqrt14[tid] : p.lut_rcp14[tid - 128];
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(mbars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
+
+    if (tid < NPT) {
+        // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+            const int buf = iter & 1;
+            unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * HH * HP;
+            unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
+            const int ty = tile / gx, tx = tile - ty * gx;
+            const int x0 = tx * TW, y0 = p.row0 + ty * th;
+            mbar_wait(mempty0 + buf, (unsigned)(((iter >> 1) & 1) ^ 1));     // the consumer is done with this bucket tile
+            const bool cols_hashed = (x0 - 1 + HW > 6) && (x0 - 1 < p.c_end);
+            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk h0 needs rows h0 .. h0+RBP+11
+            for (int idx = tid; idx < (RBP + 10) * SW; idx += NPT) {         // rows 0 .. RBP+9 up front (the chunk loop adds two more)
+                const int s = idx / SW, sx = idx - s * SW;
+                sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+            }
+            for (int h0 = 0; h0 < hh; h0 += RBP) {
+                const int rfirst = y0 - 1 + h0;
+                // two new ring rows: s = h0+RBP+10, h0+RBP+11
+                for (int idx = tid; idx < RBP * SW; idx += NPT) {
+                    const int s = h0 + RBP + 10 + idx / SW, sx = idx % SW;
+                    sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                }
+                group_sync(1, NPT);
+                const bool any_hashed = cols_hashed && (rfirst + RBP > 6) && (rfirst < H - 6);
+                if (any_hashed) {
+                    // ---- B: column chains, one position per thread (gradients straight from the ring) ----
+                    const int rl = tid / QW, q = tid - rl * QW;
+                    const int r = rfirst + rl;
+                    if (r >= 6 && r < H - 6 && h0 + rl < hh) {
+                        const int s0 = h0 + rl;                                  // S row above the first gradient row
+                        float acc[6][3];
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) acc[m][0] = acc[m][1] = acc[m][2] = 0.0f;
+                        float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
+                        const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
+                        float vcur = row[1];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
+                            const float vnext = nrow[1];
+                            const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
+                            const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
+#pragma unroll
+                            for (int m = 0; m < 6; ++m) {
+                                const float w = c_gw[i][m];
+                                const float px = fmul(gxv, w), py = fmul(gyv, w);
+                                acc[m][0] = ffma(px, gxv, acc[m][0]);
+                                acc[m][1] = ffma(px, gyv, acc[m][1]);
+                                acc[m][2] = ffma(py, gyv, acc[m][2]);
+                            }
+                            vprev = vcur; vcur = vnext; row = nrow;
+                        }
+                        float *qd = sQ + (rl * 18) * QW + q;
+#pragma unroll
+                        for (int m = 0; m < 6; ++m)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) qd[(m * 3 + k) * QW] = acc[m][k];
+                    }
+                    group_sync(1, NPT);
+                }
+                // ---- C: bucket, one pixel per thread ----
+                {
+                    const int rl = tid / QW, j = tid - rl * QW;
+                    const int h = h0 + rl;
+                    if (j < HW && h < hh) {
+                        const int r = rfirst + rl, c = x0 - 1 + j;
+                        int hv = 255, hv2 = 255;
+                        if (any_hashed && r >= 6 && r < H - 6 && c >= 6 && c < p.c_end) {
+                            float g[3];
+                            const float *qs = sQ + (rl * 18) * QW + j;
+#pragma unroll
+                            for (int k3 = 0; k3 < 3; ++k3) {
+                                float lane[11];
+#pragma unroll
+                                for (int k = 0; k < 11; ++k) {
+                                    const int m = k < 6 ? k : 10 - k;
+                                    lane[k] = qs[(m * 3 + k3) * QW + k];
+                                }
+                                g[k3] = tree_sum(lane);
+                            }
+                            if (c < p.tail_start) {
+                                hv = hash_bucket<true>(hc, g[0], g[1], g[2]);
+                            } else {
+                                hv = hash_bucket<false>(hc, g[0], g[1], g[2]);
+                                if (c < p.ov_end) {
+                                    const int h16 = hash_bucket<true>(hc, g[0], g[1], g[2]);
+                                    if (h16 != hv) hv2 = h16;
+                                }
+                            }
+                            if (p.hash_out && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
+                        }
+                        sHash[h * HP + j] = (unsigned char)hv;
+                        if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
+                    }
+                }
+                // the next chunk's ring fill overwrites rows B no longer reads; its barrier also orders C(this) before B(next)
+            }
+            group_sync(1, NPT);
+            if (tid == 0) mbar_arrive(mfull0 + buf);
+        }
+    } else {
+        // =========================== consumer: filter + blend of tile i ===========================
+        const int ct = tid - NPT;
+        const int lane = ct & 31, cwarp = ct >> 5;
+        const int g = lane >> 3, q = lane & 7;
+        constexpr int JS = (PT == 4) ? 2 : 1;
+        constexpr int U = 4;
+        constexpr int NCOLS = (HW + JS - 1) / JS;
+        constexpr int NBLK = (NCOLS + 4 * U - 1) / (4 * U);
+        constexpr int ULAST = (NCOLS - 4 * U * (NBLK - 1) + 3) / 4;
+        int off[8][2];
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 16 * m + 2 * q + e;
+                off[m][e] = (k < 121) ? (k / 11) * SP + (k % 11) : 0;
+            }
+        const float flo = (float)p.lo, fhi = (float)p.hi;
+        const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
+        const float4 *sF4 = reinterpret_cast<const float4 *>(sF) + q;
+        unsigned nload = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+            const int buf = iter & 1;
+            const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * HH * HP;
+            const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
+            const int ty = tile / gx, tx = tile - ty * gx;
+            const int x0 = tx * TW, y0 = p.row0 + ty * th;
+
+            // ---- A: S tile (the slice buffer is free until the first slice load: low-res staging for the 2x path) ----
+            if (UPS == 1) {
+                float *sL = sF;
+                const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;
+                const int lrh = (th + 14) / 2 + 1;
+                for (int idx = ct; idx < lrh * LRW; idx += NCT) {
+                    const int ly = idx / LRW, lx = idx - ly * LRW;
+                    const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
+                    sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
+                }
+                group_sync(2, NCT);
+                for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
+                    const int bi = idx / (LRW - 1) + 1, bj = idx - (bi - 1) * (LRW - 1) + 1;
+                    const float *l = sL + bi * LRP + bj;
+                    const float a0 = l[-LRP - 1], a1 = l[-LRP], b0 = l[-1], b1 = l[0];
+                    const float vo0 = ffma(3.0f, a0, b0), vo1 = ffma(3.0f, a1, b1);
+                    const float ve0 = ffma(3.0f, b0, a0), ve1 = ffma(3.0f, b1, a1);
+                    float *d = sS + (2 * bi - 2) * SP + 2 * bj - 2;
+                    d[0] = floorf(fmul(fadd(ffma(3.0f, vo0, vo1), 8.0f), 0.0625f));
+                    d[1] = floorf(fmul(fadd(ffma(3.0f, vo1, vo0), 8.0f), 0.0625f));
+                    d[SP] = floorf(fmul(fadd(ffma(3.0f, ve0, ve1), 8.0f), 0.0625f));
+                    d[SP + 1] = floorf(fmul(fadd(ffma(3.0f, ve1, ve0), 8.0f), 0.0625f));
+                }
+            } else {
+                for (int idx = ct; idx < (th + 14) * SW; idx += NCT) {
+                    const int sy = idx / SW, sx = idx - sy * SW;
+                    const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
+                    float v = 0.0f;
+                    if (Y >= 0 && Y < H && X >= 0 && X < W) v = load_S<PixT>(p, Y, X, UPS != 0);
+                    sS[sy * SP + sx] = v;
+                }
+            }
+            group_sync(2, NCT);
+            // HR := S; the filter phase overwrites accepted pixels
+            for (int idx = ct; idx < hh * HW; idx += NCT) {
+                const int h = idx / HW, j = idx - h * HW;
+                sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
+            }
+            mbar_wait(mfull0 + buf, (unsigned)((iter >> 1) & 1));             // buckets of this tile are ready
+            group_sync(2, NCT);
+
+            // ---- D: 121-tap filter, one pixel type at a time ----
+            const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
+            for (int t = 0; t < PT; ++t) {
+                if (ct == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(mslice, (unsigned)slice_bytes);
+                    const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
+                    const int piece = slice_bytes / 4;
+                    for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mslice);
+                }
+                const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;
+                const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
+                const int nrows = (hh - hfirst + JS - 1) / JS;
+                mbar_wait(mslice, nload & 1u);
+                ++nload;
+                auto block = [&](auto uu, const int h, const int jb) {
+                    constexpr int UU = decltype(uu)::value;
+                    const float *sp = sS + (h + 1) * SP + jb + 1;
+                    const unsigned char *hp = sHash + h * HP + jb;
+                    int hv[UU];
+#pragma unroll
+                    for (int u = 0; u < UU; ++u) hv[u] = (jb + 4 * JS * u < HW) ? hp[4 * JS * u] : 255;
+                    float a0[UU], a1[UU];
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        const float *q0 = sp + off[2 * n][0], *q1 = sp + off[2 * n][1], *q2 = sp + off[2 * n + 1][0], *q3 = sp + off[2 * n + 1][1];
+#pragma unroll
+                        for (int u = 0; u < UU; ++u) {
+                            const float4 f = sF4[(hv[u] == 255 ? 0 : hv[u]) * 32 + n * 8];
+                            const float p0 = q0[4 * JS * u], p1 = q1[4 * JS * u], p2 = q2[4 * JS * u], p3 = q3[4 * JS * u];
+                            if (n == 0) { a0[u] = fmul(p0, f.x); a1[u] = fmul(p1, f.y); }
+                            else { a0[u] = ffma(p0, f.x, a0[u]); a1[u] = ffma(p1, f.y, a1[u]); }
+                            a0[u] = ffma(p2, f.z, a0[u]);
+                            a1[u] = ffma(p3, f.w, a1[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UU; ++u) {
+                        const float cur = tree8(a0[u], a1[u], q);
+                        bool ok = (cur > flo) && (cur < fhi);                 // strict range test, Raisr.cpp:1192-1196
+                        float res = cur;
+                        const int j = jb + 4 * JS * u;
+                        if (has_ov) {
+                            const int c = x0 - 1 + j;
+                            const int hv2 = (j < HW && c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
+                            const bool need2 = (hv2 != 255) && !ok;
+                            if (__any_sync(0xffffffffu, need2)) {
+                                const float cur16 = dot8(sp + 4 * JS * u, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
+                                if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
+                            }
+                        }
+                        if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
+                    }
+                };
+                for (int it = cwarp; it < nrows * NBLK; it += NCW) {
+                    const int ri = it / NBLK, bi = it - ri * NBLK;
+                    const int h = hfirst + ri * JS;
+                    const int jb = jfirst + (bi * 4 * U + g) * JS;
+                    if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
+                    else block(std::integral_constant<int, ULAST>{}, h, jb);
+                }
+                group_sync(2, NCT);
+            }
+            if (ct == 0) mbar_arrive(mempty0 + buf);                          // bucket tile may be refilled (tile i+2)
+
+            // ---- E: census blend + store ----
+            for (int idx = ct; idx < th * (TW / 4); idx += NCT) {
+                const int tyy = idx / (TW / 4), txx = (idx - tyy * (TW / 4)) * 4;
+                const int Y = y0 + tyy, X = x0 + txx;
+                if (Y >= p.row1 || Y >= H || X >= W) continue;
+                float sw[3][6], hw[3][6];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const float *s = sS + (tyy + 6 + dy) * SP + txx + 6;
+                    const float *hq = sHR + (tyy + dy) * HP + txx;
+#pragma unroll
+                    for (int dx = 0; dx < 6; ++dx) { sw[dy][dx] = s[dx]; hw[dy][dx] = hq[dx]; }
+                }
+                int iv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
+                    int ham = 0;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            if (dy == 1 && dx == 1) continue;
+                            ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
+                        }
+                    const float w = fmul((float)ham, 0.125f);
+                    const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
+                                                      : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
+                    int r = min(max((int)floorf(v), p.lo), p.hi);
+                    if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;
+                    iv[e] = r;
+                }
+                PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
+                if (p.vec_store && X + 3 < W) {
+                    if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
+                    else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (X + e < W) orow[e] = (PixT)iv[e];
+                }
+            }
+            group_sync(2, NCT);                                               // S / HR are rewritten by the next tile's stage A
+            if (p.band_done && ct == 0) {
+                __threadfence();
+                atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
+            }
+        }
+    }
+}
+
+}  // namespace raisr
