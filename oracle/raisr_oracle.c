@@ -278,11 +278,30 @@ static uint16_t blend_pixel(const float *L, const float *Hh, int W, int r, int c
     return (uint16_t)iv;
 }
 
+/* ---- Randomness blend (blending = 1), Raisr.cpp:1203-1242 + CTRandomness_AVX512_32f (Raisr_AVX512.cpp:19-35) ----
+ * Applied inside the hot loop to hashed pixels only, with the value of THIS evaluation (cur = filter result if in
+ * range, else the upscale), so on the 16/8 overlap columns the 8-wide evaluation alone decides. */
+static uint16_t randomness_pixel(const float *L, int W, int r, int c, float cur, int lo, int hi, int x86)
+{
+    const float lc = L[(size_t)r * W + c];
+    int census = 0;
+    for (int i = -1; i <= 1; i++)
+        for (int j = -1; j <= 1; j++)
+            if ((i || j) && L[(size_t)(r + i) * W + c + j] < lc) census++;
+    float w = (float)census / 8.0f, w2 = 1.0f - w;
+    /* source: weight*curPix + (1-weight)*LR, then += 0.5;  as compiled: fma(w, cur, w2*LR) (w2*LR is exact), then + 0.5 */
+    float v = x86 ? fmaf(w, cur, w2 * lc) : (w * cur + w2 * lc);
+    v += 0.5f;
+    if (v < (float)lo) return (uint16_t)lo;
+    if (v > (float)hi) return (uint16_t)hi;
+    return (uint16_t)(int)v;
+}
+
 int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
                 int32_t *hash, float *gtwg, float *hr, uint16_t *out)
 {
     if (!S || !out || !p || !p->filters || W < 1 || H < 1) return -1;
-    if (p->blending != 2) return -1;    /* Randomness blending (Raisr.cpp:1203-1242) is not restated yet */
+    if (p->blending != 1 && p->blending != 2) return -1;
     if (p->nptypes != 1 && p->nptypes != 4) return -1;
     const size_t N = (size_t)W * H;
     float *L = (float *)malloc(N * sizeof(float));
@@ -295,6 +314,10 @@ int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
     float wt[11][16];
     gaussian_table(p->bits, wt);
     const float flo = (float)p->lo, fhi = (float)p->hi;
+    /* Everything the blends below do not overwrite is the integer upscale itself, unclamped (row/edge memcpys,
+     * Raisr.cpp:999-1028, 1252-1265).  With Randomness blending the reference never writes pixels
+     * (H-7, [c_end, W-6)); this restatement defines them as the upscale too. */
+    for (size_t i = 0; i < N; i++) out[i] = S[i];
 
     /* hot double loop, Raisr.cpp:1038-1066.  Blocks of 16, then blocks of 8 near the right edge; the first
      * 8-block starts 8 columns after the last 16-block, i.e. it REDOES that block's second half with the
@@ -313,6 +336,8 @@ int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
                     const float *f = p->filters + ((size_t)hv * p->nptypes + pt) * 121;
                     float cur = dot_patch(L, W, r, cc, f);
                     if (cur > flo && cur < fhi) Hh[(size_t)r * W + cc] = cur;                /* Raisr.cpp:1192-1196 */
+                    else cur = L[(size_t)r * W + cc];
+                    if (p->blending == 1) out[(size_t)r * W + cc] = randomness_pixel(L, W, r, cc, cur, p->lo, p->hi, p->sqrt_mode == ORACLE_SQRT_X86);
                     if (hash) hash[(size_t)r * W + cc] = hv;
                     if (gtwg) memcpy(gtwg + ((size_t)r * W + cc) * 3, g + 3 * q, 3 * sizeof(float));
                 }
@@ -323,9 +348,7 @@ int oracle_pass(const uint16_t *S, int W, int H, const oracle_pass_params *p,
     }
     if (hr) memcpy(hr, Hh, N * sizeof(float));
 
-    /* borders: everything the blend below does not overwrite is the integer upscale itself, unclamped
-     * (row/edge memcpys, Raisr.cpp:999-1028, 1252-1265) */
-    for (size_t i = 0; i < N; i++) out[i] = S[i];
+    if (p->blending == 2)
     for (int r = 1; r < H - 1; r++)
         for (int c = 1; c < W - 1; c++) out[(size_t)r * W + c] = blend_pixel(L, Hh, W, r, c, p->lo, p->hi, p->sqrt_mode == ORACLE_SQRT_X86);
     free(L); free(Hh);

@@ -301,10 +301,11 @@ def run_ref_subprocess(folder_name, inY, ratio=2.0, bits=8, rng=VideoRange, thre
 
 def load_golden(name):
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
-    ratio, bits, passes, mode, rng, seed = z["meta"]
+    ratio, bits, passes, mode, rng, seed = z["meta"][:6]
+    blending = int(z["meta"][6]) if len(z["meta"]) > 6 else CountOfBitsChanged
     return dict(in_y=z["in_y"], in_u=z["in_u"], in_v=z["in_v"], out_y=z["out_y"], out_u=z["out_u"], out_v=z["out_v"],
                 hash=[z["hash%d" % i].astype(np.int32) for i in range(int(passes))], ratio=float(ratio), bits=int(bits),
-                passes=int(passes), mode=int(mode), rng=int(rng), folder=str(z["folder"]), kind=str(z["kind"]))
+                passes=int(passes), mode=int(mode), rng=int(rng), folder=str(z["folder"]), kind=str(z["kind"]), blending=blending)
 
 
 def golden_names():

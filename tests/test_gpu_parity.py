@@ -116,7 +116,7 @@ def test_x86_mode_bit_identical_to_reference_golden(name):
                    numerics=B.NUMERICS_X86, keep_hash=True)
     eng.set_res(w, h, oW, oH, g["in_u"].shape[1], g["in_u"].shape[0], g["out_u"].shape[1], g["out_u"].shape[0])
     oy, ou, ov = np.zeros_like(g["out_y"]), np.zeros_like(g["out_u"]), np.zeros_like(g["out_v"])
-    assert eng.process_host(g["in_y"], oy, g["in_u"], g["in_v"], ou, ov) == 0
+    assert eng.process_host(g["in_y"], oy, g["in_u"], g["in_v"], ou, ov, blending=g["blending"]) == 0
     for i in range(g["passes"]):
         hv = eng.read_hash(i, g["hash"][i].shape[1], g["hash"][i].shape[0])
         assert np.array_equal(hv, g["hash"][i]), "pass %d buckets: %d differ" % (i, (hv != g["hash"][i]).sum())
@@ -195,3 +195,29 @@ def test_pipelined_kernel_variant_is_bit_identical(monkeypatch):
     monkeypatch.setenv("RAISR_CUDA_KERNEL", "pipe")
     pipe, hp = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
     assert np.array_equal(base, pipe) and all(np.array_equal(a, b) for a, b in zip(hb, hp))
+
+
+@pytest.mark.parametrize("numerics", [B.NUMERICS_IEEE, B.NUMERICS_X86])
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size", [
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (250, 140)),       # has pixels the reference leaves unwritten: defined as the upscale
+    ("filters_2x/filters_highres", 2.0, 10, 2, 1, (200, 120)),
+    ("filters_1.5x/filters_denoise", 1.5, 8, 2, 2, (240, 136)),
+])
+def test_randomness_blending_vs_oracle(folder, ratio, bits, passes, mode, size, numerics):
+    """blending = 1 (Randomness, Raisr.cpp:1203-1242) against the oracle, both numerics."""
+    if numerics == B.NUMERICS_X86 and not T.have_avx512():
+        pytest.skip("ORACLE_SQRT_X86 needs AVX-512 on the host")
+    w, h = size
+    f = T.filter_folder(folder)
+    img = T.synth_frame(w, h, bits, seed=808 + w, kind="mix")
+    oW, oH = int(w * ratio), int(h * ratio)
+    eng = B.Engine(f, ratio, bits, T.VideoRange, passes, mode, numerics=numerics)
+    eng.set_res(w, h, oW, oH)
+    out = np.zeros((oH, oW), img.dtype)
+    assert eng.process_host(img, out, blending=T.Randomness) == 0
+    eng.close()
+    sm = 1 if numerics == B.NUMERICS_X86 else 0
+    m1 = T.OracleModel(f, bits, False, T.VideoRange, sm, T.Randomness)
+    m2 = T.OracleModel(f, bits, True, T.VideoRange, sm, T.Randomness) if passes == 2 else None
+    ref = T.oracle_process_y(img, oW, oH, m1, m2, passes, mode)
+    assert np.array_equal(out, ref), "Y differs on %d px" % (out != ref).sum()

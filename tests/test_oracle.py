@@ -11,8 +11,8 @@ needs_avx512 = pytest.mark.skipif(not T.have_avx512(), reason="ORACLE_SQRT_X86 e
 
 def run_oracle(g, sqrt_mode):
     f = T.filter_folder(g["folder"])
-    m1 = T.OracleModel(f, g["bits"], False, g["rng"], sqrt_mode)
-    m2 = T.OracleModel(f, g["bits"], True, g["rng"], sqrt_mode) if g["passes"] == 2 else None
+    m1 = T.OracleModel(f, g["bits"], False, g["rng"], sqrt_mode, g["blending"])
+    m2 = T.OracleModel(f, g["bits"], True, g["rng"], sqrt_mode, g["blending"]) if g["passes"] == 2 else None
     h, w = g["in_y"].shape
     return T.oracle_process_y(g["in_y"], int(w * g["ratio"]), int(h * g["ratio"]), m1, m2, g["passes"], g["mode"], want_hash=True)
 

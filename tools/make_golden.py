@@ -27,6 +27,10 @@ CASES = [
     ("highres_15x_8b_p1", "filters_1.5x/filters_highres", 1.5, 8, 1, 1, T.VideoRange, (160, 90), "mix", 17),
     ("denoise_15x_8b_p2m2", "filters_1.5x/filters_denoise", 1.5, 8, 2, 2, T.VideoRange, (142, 80), "noise", 18),
     ("lowres_2x_8b_flat", "filters_2x/filters_lowres", 2.0, 8, 1, 1, T.VideoRange, (96, 64), "flat", 19),
+    # blending = 1 (Randomness); width chosen so that the pixels the reference leaves unwritten (row H-7, columns
+    # [c_end, W-6)) do not exist: c_end == W-6
+    ("lowres_2x_8b_p1_randomness", "filters_2x/filters_lowres", 2.0, 8, 1, 1, T.VideoRange, (154, 88), "mix", 20, T.Randomness),
+    ("highres_15x_8b_p1_randomness", "filters_1.5x/filters_highres", 1.5, 8, 1, 1, T.FullRange, (168, 90), "noise", 21, T.Randomness),
 ]
 
 
@@ -44,7 +48,9 @@ def main():
     hp = (C.c_void_p * 2).in_dll(L, "g_raisr_dbg_hash")
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    for name, folder, ratio, bits, passes, mode, rng, (w, h), kind, seed in [c for c in CASES if c[0] == sys.argv[1]]:
+    for case in [c for c in CASES if c[0] == sys.argv[1]]:
+        name, folder, ratio, bits, passes, mode, rng, (w, h), kind, seed = case[:10]
+        blending = case[10] if len(case) > 10 else T.CountOfBitsChanged
         img = T.synth_frame(w, h, bits, seed, kind)
         u, v = T.synth_chroma(w // 2, h // 2, bits, seed + 100), T.synth_chroma(w // 2, h // 2, bits, seed + 200)
         oW, oH = int(w * ratio), int(h * ratio)
@@ -55,10 +61,10 @@ def main():
             hp[i] = planes[-1].ctypes.data
         for i in range(passes, 2):
             hp[i] = None
-        oy, ou, ov = T.run_handler(L, T.filter_folder(folder), img, ratio, bits, rng, 1, T.AVX512, passes, mode, inU=u, inV=v)
+        oy, ou, ov = T.run_handler(L, T.filter_folder(folder), img, ratio, bits, rng, 1, T.AVX512, passes, mode, blending=blending, inU=u, inV=v)
         hp[0] = hp[1] = None
         d = {"in_y": img, "in_u": u, "in_v": v, "out_y": oy, "out_u": ou, "out_v": ov,
-             "meta": np.array([ratio, bits, passes, mode, rng, seed], np.float64), "folder": np.array(folder), "kind": np.array(kind)}
+             "meta": np.array([ratio, bits, passes, mode, rng, seed, blending], np.float64), "folder": np.array(folder), "kind": np.array(kind)}
         for i, pl in enumerate(planes):
             d["hash%d" % i] = pl.astype(np.int16)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **d)

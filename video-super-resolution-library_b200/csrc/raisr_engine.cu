@@ -121,6 +121,7 @@ struct raisr_cuda_engine {
     int lo = 0, hi = 255;
     int device = 0;
     int num_sms = 148;
+    int blending = 2;               // BlendingMode of the frame being processed
     bool use_pipe = false;          // RAISR_CUDA_KERNEL=pipe selects the warp-specialised persistent kernel (measured: no faster)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
@@ -256,7 +257,7 @@ void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
     }
     p->nangles = e->model.q_angle;
     p->hash_out = e->d_hash[pass_idx];
-    p->blending = 2;
+    p->blending = e->blending;
     p->lut_rsqrt14 = static_cast<const uint2 *>(e->d_lut[0]); p->lut_rcp14 = static_cast<const uint2 *>(e->d_lut[1]);
     p->lut_rsqrtps = static_cast<const uint16_t *>(e->d_lut[2]); p->lut_rcpps = static_cast<const uint16_t *>(e->d_lut[3]);
 }
@@ -305,8 +306,8 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
 
 int check_blending(int blending)
 {
-    if (blending == CountOfBitsChanged) return 0;
-    std::cout << "[RAISR ERROR] blending mode " << blending << " is not available in the CUDA engine (only CountOfBitsChanged = 2)" << std::endl;
+    if (blending == CountOfBitsChanged || blending == Randomness) return 0;
+    std::cout << "[RAISR ERROR] unknown blending mode " << blending << std::endl;
     return RNLErrorBadParameter;
 }
 
@@ -482,6 +483,7 @@ int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_
 {
     if (!e || !e->have_res || !in_y || !out_y || row0 >= row1 || row1 > (unsigned)e->out_h) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
+    e->blending = blending;
     CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (unsigned i = 0; i < e->cfg.passes; ++i)
@@ -508,6 +510,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
 {
     if (!e || !e->have_res || !in_y || !out_y) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
+    e->blending = blending;
     CUDA_OK(cudaSetDevice(e->device));
     const size_t bps = e->bps;
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;

@@ -410,6 +410,77 @@ __device__ __forceinline__ float dot8(const float *sp, const float *frow, const 
     return tree8(a0, a1, q);          // same value in the pixel's 8 lanes
 }
 
+// ---- stage E: blend + store, one thread = 4 consecutive pixels of a row (a 3x6 window of S and of HR, one vector store)
+// blending 2: CTCountOfBitsChangedSegment_AVX256_32f (Raisr_AVX256.cpp:68-166) over rows/cols [1, dim-1); the 1-px frame is
+//             the integer upscale itself (Raisr.cpp:999-1028,1252-1265).
+// blending 1: Randomness (Raisr.cpp:1203-1242, CTRandomness_AVX512_32f Raisr_AVX512.cpp:19-35) on hashed pixels only,
+//             everything else is the integer upscale (border memcpys).
+template <typename PixT>
+__device__ __forceinline__ void stage_blend_store(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
+                                                  int x0, int y0, int th, int t0, int nthreads)
+{
+    const int W = p.W, H = p.H;
+    for (int idx = t0; idx < th * (TW / 4); idx += nthreads) {
+        const int ty = idx / (TW / 4), tx = (idx - ty * (TW / 4)) * 4;
+        const int Y = y0 + ty, X = x0 + tx;
+        if (Y >= p.row1 || Y >= H || X >= W) continue;
+        float sw[3][6], hw[3][6];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const float *s = sS + (ty + 6 + dy) * SP + tx + 6;
+            const float *hq = sHR + (ty + dy) * HP + tx;
+#pragma unroll
+            for (int dx = 0; dx < 6; ++dx) { sw[dy][dx] = s[dx]; hw[dy][dx] = hq[dx]; }
+        }
+        int iv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
+            int r;
+            if (p.blending == 2) {
+                int ham = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (dy == 1 && dx == 1) continue;
+                        ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
+                    }
+                const float w = fmul((float)ham, 0.125f);
+                // source semantics: (w*LR + (1-w)*HR) + 0.5; as compiled (-ffast-math): fma(1-w, HR, fma(LR, w, 0.5)), one rounding
+                const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
+                                                  : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
+                r = min(max((int)floorf(v), p.lo), p.hi);
+                if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;   // 1-px frame
+            } else {
+                int census = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (dy == 1 && dx == 1) continue;
+                        census += (sw[dy][e + dx] < lc);
+                    }
+                const float w = fmul((float)census, 0.125f), w2 = fsub(1.0f, w);
+                // source: w*cur + (1-w)*LR, += 0.5; as compiled: fma(w, cur, (1-w)*LR) then + 0.5   (hcv = this pixel's cur)
+                const float v = fadd((p.numerics == 0) ? fadd(fmul(w, hcv), fmul(w2, lc)) : ffma(w, hcv, fmul(w2, lc)), 0.5f);
+                r = (v < (float)p.lo) ? p.lo : ((v > (float)p.hi) ? p.hi : (int)v);
+                if (sHash[(ty + 1) * HP + tx + 1 + e] == 255) r = (int)lc;               // not hashed: border copy of the upscale
+            }
+            iv[e] = r;
+        }
+        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
+        if (p.vec_store && X + 3 < W) {
+            if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
+            else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (X + e < W) orow[e] = (PixT)iv[e];
+        }
+    }
+}
+
 // UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),
 //      2 = any ratio through the per-axis tables (1.5x).   PT: pixel types (4 at 2x, else 1).
 template <typename PixT, int PT, int UPS>
@@ -630,7 +701,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     if (has_ov) {                                 // tile holds columns hashed by both variants (rare path)
                         const int c = x0 - 1 + j;
                         const int hv2 = (j < HW && c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
-                        const bool need2 = (hv2 != 255) && !ok;
+                        const bool need2 = (hv2 != 255) && !ok && p.blending == 2;   // Randomness blends this evaluation only
                         if (__any_sync(0xffffffffu, need2)) {
                             const float cur16 = dot8(sp + 4 * JS * u, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
                             if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
@@ -650,50 +721,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
         }
     }
 
-    // ---- E: census blend + store (CTCountOfBitsChangedSegment_AVX256_32f, Raisr_AVX256.cpp:68-166) ----
-    // one thread = 4 consecutive pixels of a row: a 3x6 window of S and of HR, one vector store
-    for (int idx = tid; idx < th * (TW / 4); idx += NT) {
-        const int ty = idx / (TW / 4), tx = (idx - ty * (TW / 4)) * 4;
-        const int Y = y0 + ty, X = x0 + tx;
-        if (Y >= p.row1 || Y >= H || X >= W) continue;
-        float sw[3][6], hw[3][6];
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const float *s = sS + (ty + 6 + dy) * SP + tx + 6;
-            const float *hq = sHR + (ty + dy) * HP + tx;
-#pragma unroll
-            for (int dx = 0; dx < 6; ++dx) { sw[dy][dx] = s[dx]; hw[dy][dx] = hq[dx]; }
-        }
-        int iv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
-            int ham = 0;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    if (dy == 1 && dx == 1) continue;
-                    ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
-                }
-            const float w = fmul((float)ham, 0.125f);
-            // source semantics: (w*LR + (1-w)*HR) + 0.5; as compiled (-ffast-math): fma(1-w, HR, fma(LR, w, 0.5)), one rounding
-            const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
-                                              : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
-            int r = min(max((int)floorf(v), p.lo), p.hi);
-            if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;   // 1-px frame: the integer upscale itself (Raisr.cpp:999-1028,1252-1265)
-            iv[e] = r;
-        }
-        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
-        if (p.vec_store && X + 3 < W) {
-            if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
-            else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (X + e < W) orow[e] = (PixT)iv[e];
-        }
-    }
+    stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, tid, NT);
     // row-band completion signal: the host's D2H stream waits (cuStreamWaitValue32) for all tiles of a band
     if (p.band_done) {
         __syncthreads();

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams
                         if (has_ov) {
                             const int c = x0 - 1 + j;
                             const int hv2 = (j < HW && c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
-                            const bool need2 = (hv2 != 255) && !ok;
+                            const bool need2 = (hv2 != 255) && !ok && p.blending == 2;
                             if (__any_sync(0xffffffffu, need2)) {
                                 const float cur16 = dot8(sp + 4 * JS * u, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
                                 if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
@@ -328,51 +328,10 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams
                 }
                 group_sync(2, NCT);
             }
-            if (ct == 0) mbar_arrive(mempty0 + buf);                          // bucket tile may be refilled (tile i+2)
-
-            // ---- E: census blend + store ----
-            for (int idx = ct; idx < th * (TW / 4); idx += NCT) {
-                const int tyy = idx / (TW / 4), txx = (idx - tyy * (TW / 4)) * 4;
-                const int Y = y0 + tyy, X = x0 + txx;
-                if (Y >= p.row1 || Y >= H || X >= W) continue;
-                float sw[3][6], hw[3][6];
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const float *s = sS + (tyy + 6 + dy) * SP + txx + 6;
-                    const float *hq = sHR + (tyy + dy) * HP + txx;
-#pragma unroll
-                    for (int dx = 0; dx < 6; ++dx) { sw[dy][dx] = s[dx]; hw[dy][dx] = hq[dx]; }
-                }
-                int iv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
-                    int ham = 0;
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            if (dy == 1 && dx == 1) continue;
-                            ham += ((sw[dy][e + dx] < lc) != (hw[dy][e + dx] < hcv));
-                        }
-                    const float w = fmul((float)ham, 0.125f);
-                    const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
-                                                      : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
-                    int r = min(max((int)floorf(v), p.lo), p.hi);
-                    if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;
-                    iv[e] = r;
-                }
-                PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
-                if (p.vec_store && X + 3 < W) {
-                    if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
-                    else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (X + e < W) orow[e] = (PixT)iv[e];
-                }
-            }
+            // ---- E: blend + store ----
+            stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
             group_sync(2, NCT);                                               // S / HR are rewritten by the next tile's stage A
+            if (ct == 0) mbar_arrive(mempty0 + buf);                          // bucket tile may be refilled (tile i+2)
             if (p.band_done && ct == 0) {
                 __threadfence();
                 atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
