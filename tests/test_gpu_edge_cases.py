@@ -1,0 +1,133 @@
+"""GPU edge cases: tiny and ragged frames, 16-bit depth, other chroma samplings, odd 1.5x sizes, the remaining
+BASELINE configurations at full size (properties + oracle slabs)."""
+import importlib.util
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import raisr_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+_spec = importlib.util.spec_from_file_location("raisr_binding", os.path.join(T.PKG_DIR, "binding.py"))
+B = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(B)
+
+X86 = T.have_avx512()
+NUM = B.NUMERICS_X86 if X86 else B.NUMERICS_IEEE
+SM = 1 if X86 else 0
+
+
+def engine_run(folder, img, ratio, bits, passes=1, mode=1, rng=T.VideoRange, out_hw=None):
+    h, w = img.shape
+    oW, oH = out_hw if out_hw else (int(w * ratio), int(h * ratio))
+    eng = B.Engine(folder, ratio, bits, rng, passes, mode, numerics=NUM)
+    eng.set_res(w, h, oW, oH)
+    out = np.zeros((oH, oW), img.dtype)
+    assert eng.process_host(img, out) == 0
+    eng.close()
+    return out
+
+
+def oracle_run(folder, img, ratio, bits, passes=1, mode=1, rng=T.VideoRange, out_hw=None):
+    h, w = img.shape
+    oW, oH = out_hw if out_hw else (int(w * ratio), int(h * ratio))
+    m1 = T.OracleModel(folder, bits, False, rng, SM)
+    m2 = T.OracleModel(folder, bits, True, rng, SM) if passes == 2 else None
+    return T.oracle_process_y(img, oW, oH, m1, m2, passes, mode)
+
+
+@pytest.mark.parametrize("size", [(4, 4), (10, 10), (13, 7), (14, 20), (15, 15), (31, 17), (57, 9), (101, 57), (117, 35), (119, 64)])
+def test_tiny_and_ragged_2x(size):
+    """Frames narrower than one 16-block hash nothing (c_end == 6); tiles with 1..4 valid columns; odd widths (no vector stores)."""
+    w, h = size
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = T.synth_frame(w, h, 8, seed=w * 131 + h, kind="noise")
+    assert np.array_equal(engine_run(f, img, 2.0, 8), oracle_run(f, img, 2.0, 8))
+
+
+@pytest.mark.parametrize("size", [(22, 14), (100, 66), (202, 118)])
+def test_ratio_15_sizes(size):
+    w, h = size
+    f = T.filter_folder("filters_1.5x/filters_highres")
+    img = T.synth_frame(w, h, 8, seed=w + h, kind="mix")
+    assert np.array_equal(engine_run(f, img, 1.5, 8), oracle_run(f, img, 1.5, 8))
+
+
+@pytest.mark.skipif(not (T.have_ref() and X86), reason="needs the compiled reference on an AVX-512 host")
+def test_odd_15x_geometry_vs_live_reference():
+    """101x67 -> 151x100: the reference's resize spec maps (int)(outH/ratio) = 66 source rows, not 67 (Raisr.cpp:1801-1803)."""
+    img = T.synth_frame(101, 67, 8, seed=9, kind="mix")
+    ref_y, _ = T.run_ref_subprocess("filters_1.5x/filters_highres", img, 1.5, 8)
+    out = engine_run(T.filter_folder("filters_1.5x/filters_highres"), img, 1.5, 8)
+    assert out.shape == ref_y.shape and np.array_equal(out, ref_y), "Y differs on %d px" % (out != ref_y).sum()
+
+
+def test_16bit_depth(tmp_path):
+    """No 16-bit model is shipped; a folder with the 10-bit tables renamed exercises the 16-bit code path
+    (NF_16 Gaussian, 0..65535 range, u16 planes, Raisr.cpp:1462-1468)."""
+    src = T.filter_folder("filters_2x/filters_highres")
+    dst = tmp_path / "model16"
+    os.makedirs(dst)
+    shutil.copy(os.path.join(src, "config"), dst / "config")
+    for stem in ("filterbin_2_", "Qfactor_strbin_2_", "Qfactor_cohbin_2_"):
+        shutil.copy(os.path.join(src, stem + "10"), dst / (stem + "16"))
+    rs = np.random.RandomState(5)
+    base = T.synth_frame(120, 80, 10, seed=3).astype(np.uint32) * 64
+    img = np.clip(base + rs.randint(0, 64, size=base.shape), 0, 65535).astype(np.uint16)
+    assert np.array_equal(engine_run(str(dst), img, 2.0, 16), oracle_run(str(dst), img, 2.0, 16))
+
+
+@pytest.mark.parametrize("shift", [(1, 1), (1, 0), (0, 0)])     # 4:2:0, 4:2:2, 4:4:4 (vf_raisr.c:158-162,191-204)
+def test_chroma_samplings_through_handler(shift):
+    f = T.filter_folder("filters_2x/filters_lowres")
+    w, h = 128, 72
+    cw, ch = w >> shift[0], h >> shift[1]
+    y = T.synth_frame(w, h, 8, seed=1)
+    u, v = T.synth_chroma(cw, ch, 8, 2), T.synth_chroma(cw, ch, 8, 3)
+    L = T.handler_lib(T.product_lib_path())
+    oy, ou, ov = T.run_handler(L, f, y, inU=u, inV=v, chroma_shift=shift)
+    assert ou.shape == (2 * ch, 2 * cw)
+    assert np.array_equal(ou, T.oracle_resize(u, 2 * cw, 2 * ch)) and np.array_equal(ov, T.oracle_resize(v, 2 * cw, 2 * ch))
+
+
+def slab_check(folder, img, out, ratio, bits, passes, mode, lr0, lr_rows, margin_lr):
+    """Runs the oracle on input rows [lr0, lr0+lr_rows) and compares the output rows that cannot see the slab edges."""
+    ref = oracle_run(folder, img[lr0:lr0 + lr_rows], ratio, bits, passes, mode)
+    a = int(margin_lr * ratio)
+    o0 = int(lr0 * ratio)
+    got = out[o0 + a:o0 + ref.shape[0] - a]
+    assert np.array_equal(got, ref[a:-a]), "slab differs on %d px" % (got != ref[a:-a]).sum()
+
+
+def test_config3_1080p_to_4k_highres_two_pass():
+    """BASELINE configs[2] at full size: invariants + a slab against the oracle (two passes: 14 output rows of reach per pass)."""
+    f = T.filter_folder("filters_2x/filters_highres")
+    img = T.synth_frame(1920, 1080, 8, seed=21)
+    out = engine_run(f, img, 2.0, 8, passes=2, mode=1)
+    assert out[1:-1, 1:-1].min() >= 16 and out[1:-1, 1:-1].max() <= 235
+    slab_check(f, img, out, 2.0, 8, 2, 1, lr0=500, lr_rows=96, margin_lr=16)
+
+
+def test_config4_4k_to_8k_denoise_10bit_two_pass_mode2():
+    """BASELINE configs[3] at full size (single GPU): 3840x2160 -> 7680x4320, 10-bit, passes=2 mode=2."""
+    f = T.filter_folder("filters_2x/filters_denoise")
+    img = T.synth_frame(3840, 2160, 10, seed=22)
+    out = engine_run(f, img, 2.0, 10, passes=2, mode=2)
+    assert out.shape == (4320, 7680)
+    assert out[1:-1, 1:-1].min() >= 64 and out[1:-1, 1:-1].max() <= 940
+    slab_check(f, img, out, 2.0, 10, 2, 2, lr0=1000, lr_rows=64, margin_lr=20)
+
+
+def test_config5_720p_to_1080p_15x():
+    """BASELINE configs[4] geometry with a folder that ships the needed tables (filters_1.5x/filters_denoise, 2 passes)."""
+    f = T.filter_folder("filters_1.5x/filters_denoise")
+    img = T.synth_frame(1280, 720, 8, seed=23)
+    out = engine_run(f, img, 1.5, 8, passes=2, mode=2)
+    assert out.shape == (1080, 1920)
+    slab_check(f, img, out, 1.5, 8, 2, 2, lr0=300, lr_rows=96, margin_lr=24)
+    # the folder BASELINE names for this config has no second-pass tables: same failure as the reference
+    with pytest.raises(RuntimeError):
+        B.Engine(T.filter_folder("filters_1.5x/filters_highres"), 1.5, 8, T.VideoRange, 2, 1)

@@ -415,8 +415,8 @@ __device__ __forceinline__ float dot8(const float *sp, const float *frow, const 
 //             the integer upscale itself (Raisr.cpp:999-1028,1252-1265).
 // blending 1: Randomness (Raisr.cpp:1203-1242, CTRandomness_AVX512_32f Raisr_AVX512.cpp:19-35) on hashed pixels only,
 //             everything else is the integer upscale (border memcpys).
-template <typename PixT>
-__device__ __forceinline__ void stage_blend_store(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
+template <typename PixT, int BL>
+__device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
                                                   int x0, int y0, int th, int t0, int nthreads)
 {
     const int W = p.W, H = p.H;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void stage_blend_store(const PassParams &p, const flo
         for (int e = 0; e < 4; ++e) {
             const float lc = sw[1][e + 1], hcv = hw[1][e + 1];
             int r;
-            if (p.blending == 2) {
+            if (BL == 2) {
                 int ham = 0;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
@@ -479,6 +479,14 @@ __device__ __forceinline__ void stage_blend_store(const PassParams &p, const flo
                 if (X + e < W) orow[e] = (PixT)iv[e];
         }
     }
+}
+
+template <typename PixT>
+__device__ __forceinline__ void stage_blend_store(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
+                                                  int x0, int y0, int th, int t0, int nthreads)
+{
+    if (p.blending == 2) stage_blend_store_t<PixT, 2>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
+    else stage_blend_store_t<PixT, 1>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
 }
 
 // UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),
