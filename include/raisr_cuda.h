@@ -64,7 +64,8 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
 
 /* Row-band form of the luma path for multi-GPU sharding (the reference's per-thread bands, Raisr.cpp:1738-1779):
  * computes output rows [row0, row1) only; in_y still points at row 0 of the full input plane, of which only
- * the rows the band depends on are read (single-pass configurations). */
+ * the rows the band depends on are read.  With two passes the first pass is recomputed on the rows the second can
+ * reach (overlap-recompute), so bands need no halo exchange. */
 int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, void *out_y,
                                    size_t out_y_step, int blending, unsigned row0, unsigned row1, void *stream);
 

@@ -131,3 +131,32 @@ def test_config5_720p_to_1080p_15x():
     # the folder BASELINE names for this config has no second-pass tables: same failure as the reference
     with pytest.raises(RuntimeError):
         B.Engine(T.filter_folder("filters_1.5x/filters_highres"), 1.5, 8, T.VideoRange, 2, 1)
+
+
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode", [
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1),
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2),
+    ("filters_1.5x/filters_denoise", 1.5, 8, 2, 2),
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1),
+])
+def test_row_bands_reproduce_full_frame(folder, ratio, bits, passes, mode):
+    """Row-band launches (the multi-GPU shard unit) == one full-frame launch, bit for bit, including two-pass
+    configurations where pass 1 is recomputed on the rows pass 2 can reach."""
+    import torch
+    f = T.filter_folder(folder)
+    w, h = 400, 260
+    img = T.synth_frame(w, h, bits, seed=77, kind="mix")
+    oW, oH = int(w * ratio), int(h * ratio)
+    full = engine_run(f, img, ratio, bits, passes, mode)
+    eng = B.Engine(f, ratio, bits, T.VideoRange, passes, mode, numerics=NUM)
+    eng.set_res(w, h, oW, oH)
+    tdt = torch.uint8 if bits == 8 else torch.int16
+    d_in = torch.from_numpy(img.view(np.int16) if bits != 8 else img).cuda()
+    d_out = torch.zeros((oH, oW), dtype=tdt, device="cuda")
+    for r0, r1 in [(0, 100), (100, 102), (102, 258), (258, oH)]:
+        assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * d_in.element_size(), d_out.data_ptr(),
+                                       d_out.stride(0) * d_out.element_size(), r0, r1) == 0
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(img.dtype)
+    eng.close()
+    assert np.array_equal(got, full), "bands differ from the full frame on %d px" % (got != full).sum()

@@ -285,17 +285,26 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         p.band_done = band_done;
         return launch_pass(e, p, s);
     }
+    // Two passes on a row band: pass 1 is recomputed on the rows pass 2 can reach (+-7 output rows of pass 2, mapped back
+    // through the upscale in mode 2), so bands stay independent -- overlap-recompute instead of a halo exchange.
+    int m0 = 0, m1 = e->d_mid.h;
     if (row0 != 0 || row1 != e->out_h) {
-        std::cout << "[RAISR ERROR] row bands are only available with passes=1" << std::endl;
-        return RNLErrorBadParameter;
+        const int lo = std::max(0, row0 - 7), hi = std::min(e->out_h, row1 + 7);
+        if (mode2) {
+            m0 = std::max(0, (int)std::floor(lo / e->cfg.ratio) - 2);
+            m1 = std::min(e->d_mid.h, (int)std::ceil(hi / e->cfg.ratio) + 2);
+        } else {
+            m0 = lo & ~1;
+            m1 = hi;
+        }
     }
     PassParams p1{}, p2{};
     p1.in = in_y; p1.in_pitch = in_step; p1.in_w = e->in_w; p1.in_h = e->in_h;
-    p1.out = e->d_mid.ptr; p1.out_pitch = e->d_mid.pitch; p1.W = e->d_mid.w; p1.H = e->d_mid.h; p1.row0 = 0; p1.row1 = p1.H;
+    p1.out = e->d_mid.ptr; p1.out_pitch = e->d_mid.pitch; p1.W = e->d_mid.w; p1.H = e->d_mid.h; p1.row0 = m0; p1.row1 = m1;
     pass_common(e, 0, p1.W, &p1);
     if (!mode2) set_upscale(e, &p1);
     p2.in = e->d_mid.ptr; p2.in_pitch = e->d_mid.pitch; p2.in_w = e->d_mid.w; p2.in_h = e->d_mid.h;
-    p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = 0; p2.row1 = p2.H;
+    p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = row0; p2.row1 = row1;
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
     p2.band_done = band_done;
