@@ -122,6 +122,7 @@ struct raisr_cuda_engine {
     int device = 0;
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
+    int zero_copy = 2;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (measured +4 % end to end); RAISR_CUDA_ZERO_COPY overrides
     bool use_pipe = false;          // RAISR_CUDA_KERNEL=pipe selects the warp-specialised persistent kernel (measured: no faster)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
@@ -313,6 +314,16 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     return launch_pass(e, p2, s);
 }
 
+// true (and the device alias) when p is page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)
+bool mapped_host_pointer(const void *p, const void **dev)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
 int check_blending(int blending)
 {
     if (blending == CountOfBitsChanged || blending == Randomness) return 0;
@@ -381,6 +392,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     }
     if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
+    if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "pipe") == 0;
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
@@ -538,16 +550,32 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
                                       cudaMemcpyDeviceToHost, e->stream_uv));
         }
     }
-    CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    // Pinned (page-locked, device-mapped) caller planes can be used in place: the pass kernel reads the input tile
+    // rows / writes the finished 4-pixel groups straight over PCIe, spread over the whole kernel, instead of a serial
+    // H2D before and D2H copies after it.  Pageable planes (FFmpeg's default allocator) go through the copy pipeline.
+    const void *k_in = e->d_in[0].ptr;
+    size_t k_in_step = e->d_in[0].pitch;
+    void *k_out = e->d_out[0].ptr;
+    size_t k_out_step = e->d_out[0].pitch;
+    const bool in_direct = (e->zero_copy & 1) && mapped_host_pointer(in_y, &k_in);
+    if (in_direct) k_in_step = in_y_step;
+    else CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    const void *out_dev = nullptr;
+    const bool out_direct = (e->zero_copy & 2) && mapped_host_pointer(out_y, &out_dev);
+    if (out_direct) { k_out = const_cast<void *>(out_dev); k_out_step = out_y_step; }
     for (unsigned i = 0; i < e->cfg.passes; ++i)
         if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
-    const bool pipelined = e->wait_value32 != nullptr && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
-    if (pipelined) {
+    const bool pipelined = !out_direct && e->wait_value32 != nullptr && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
+    if (out_direct) {
+        int rc = run_luma(e, k_in, k_in_step, k_out, k_out_step, 0, e->out_h, e->stream);
+        if (rc) return rc;
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+    } else if (pipelined) {
         // The final pass counts finished tiles per row band; the D2H stream waits on each counter and copies that band
         // while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
         CUDA_OK(cudaMemsetAsync(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands, e->stream));
         CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
-        int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done);
         if (rc) return rc;
         CUDA_OK(cudaStreamWaitEvent(e->stream_d2h, e->ev_in, 0));      // counters are zeroed before anybody waits on them
         const int gx = (e->out_w + TW - 1) / TW;
@@ -566,7 +594,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
         CUDA_OK(cudaStreamSynchronize(e->stream));
     } else {
-        int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
         if (rc) return rc;
         CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
         CUDA_OK(cudaStreamSynchronize(e->stream));
