@@ -122,7 +122,9 @@ struct raisr_cuda_engine {
     int device = 0;
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
+    int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
     int zero_copy = 2;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (measured +4 % end to end); RAISR_CUDA_ZERO_COPY overrides
+    int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
     bool use_pipe = false;          // RAISR_CUDA_KERNEL=pipe selects the warp-specialised persistent kernel (measured: no faster)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
@@ -143,7 +145,10 @@ struct raisr_cuda_engine {
     unsigned *d_band_done = nullptr;
     cudaStream_t stream_d2h = nullptr;
     typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
-    WaitValue32Fn wait_value32 = nullptr;
+    WaitValue32Fn wait_value32 = nullptr, write_value32 = nullptr;
+    unsigned *d_in_ready = nullptr;      // per input band: sequence number of the last frame whose rows have arrived
+    unsigned frame_seq = 0;
+    cudaStream_t stream_h2d = nullptr;
     int last_grid_y = 0, last_tile_h = 0;   // geometry of the most recent pass launch
 };
 
@@ -175,7 +180,8 @@ int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStre
 {
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         CUDA_OK(cudaFuncSetAttribute(raisr_pass_pipe_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES));
         attr_done = true;
     }
@@ -183,8 +189,17 @@ int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStre
         // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
         const int ntiles = (int)(grid.x * grid.y);
         raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NT, PIPE_SMEM_BYTES, s>>>(q);
+    } else if (e->cluster == 2 && (grid.x % 2 == 0)) {
+        // pairs of horizontally neighbouring tiles form a thread-block cluster and share every filter-slice load
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        CUDA_OK(cudaLaunchKernelEx(&cfg, raisr_pass_kernel<PixT, PT, UPS, 2>, q));
     } else {
-        raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
+        raisr_pass_kernel<PixT, PT, UPS, 1><<<grid, NT, SMEM_BYTES, s>>>(q);
     }
     CUDA_OK(cudaGetLastError());
     e->launches++;
@@ -273,7 +288,7 @@ void set_upscale(const raisr_cuda_engine *e, PassParams *p)
 
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
-             cudaStream_t s, unsigned *band_done = nullptr)
+             cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0)
 {
     const bool two = e->cfg.passes == 2;
     const bool mode2 = two && e->cfg.two_pass_mode == 2;
@@ -284,6 +299,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
         p.band_done = band_done;
+        p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_band_rows = in_band_rows;
         return launch_pass(e, p, s);
     }
     // Two passes on a row band: pass 1 is recomputed on the rows pass 2 can reach (+-7 output rows of pass 2, mapped back
@@ -309,6 +325,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
     p2.band_done = band_done;
+    p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows;
     int rc = launch_pass(e, p1, s);
     if (rc) return rc;
     return launch_pass(e, p2, s);
@@ -393,6 +410,8 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
     if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
+    if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
+    if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "pipe") == 0;
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
@@ -436,7 +455,10 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
                 return fail(RNLErrorInsufficientResources);
     }
     if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
-    if (cudaMalloc(&e->d_band_done, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+    if (cudaMalloc(&e->d_in_ready, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+        cudaMemset(e->d_in_ready, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&e->d_band_done, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking) != cudaSuccess)
         return fail(RNLErrorInsufficientResources);
     {
@@ -445,6 +467,11 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             e->wait_value32 = reinterpret_cast<raisr_cuda_engine::WaitValue32Fn>(fn);
+        else
+            cudaGetLastError();
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            e->write_value32 = reinterpret_cast<raisr_cuda_engine::WaitValue32Fn>(fn);
         else
             cudaGetLastError();
     }
@@ -559,7 +586,36 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     size_t k_out_step = e->d_out[0].pitch;
     const bool in_direct = (e->zero_copy & 1) && mapped_host_pointer(in_y, &k_in);
     if (in_direct) k_in_step = in_y_step;
-    else CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    const unsigned *in_ready = nullptr;
+    int in_band_rows = 0;
+    bool banded_h2d = false;
+    if (!in_direct) {
+        const int nb = e->h2d_bands;
+        if (nb > 1 && e->write_value32 && !e->use_pipe) {
+            // banded H2D on its own stream; after each band the stream writes this frame's sequence number into the band's
+            // flag.  The pass kernel is launched FIRST and each tile waits only for the input rows it reads.
+            ++e->frame_seq;
+            in_band_rows = (e->in_h + nb - 1) / nb;
+            in_ready = e->d_in_ready;
+            banded_h2d = true;
+        } else {
+            CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+        }
+    }
+    auto enqueue_h2d_bands = [&]() -> int {
+        if (!banded_h2d) return 0;
+        for (int b = 0; b * in_band_rows < e->in_h; ++b) {
+            const int r0 = b * in_band_rows, rows = std::min(in_band_rows, e->in_h - r0);
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)r0 * e->d_in[0].pitch, e->d_in[0].pitch,
+                                      static_cast<const char *>(in_y) + (size_t)r0 * in_y_step, in_y_step, e->in_w * bps, rows,
+                                      cudaMemcpyHostToDevice, e->stream_h2d));
+            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)(e->d_in_ready + b), e->frame_seq, 0) != 0) {
+                std::cout << "[RAISR ERROR] cuStreamWriteValue32 failed" << std::endl;
+                return RNLErrorUndefined;
+            }
+        }
+        return 0;
+    };
     const void *out_dev = nullptr;
     const bool out_direct = (e->zero_copy & 2) && mapped_host_pointer(out_y, &out_dev);
     if (out_direct) { k_out = const_cast<void *>(out_dev); k_out_step = out_y_step; }
@@ -567,16 +623,18 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
     const bool pipelined = !out_direct && e->wait_value32 != nullptr && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
     if (out_direct) {
-        int rc = run_luma(e, k_in, k_in_step, k_out, k_out_step, 0, e->out_h, e->stream);
+        int rc = run_luma(e, k_in, k_in_step, k_out, k_out_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows);
         if (rc) return rc;
+        if ((rc = enqueue_h2d_bands())) return rc;
         CUDA_OK(cudaStreamSynchronize(e->stream));
     } else if (pipelined) {
         // The final pass counts finished tiles per row band; the D2H stream waits on each counter and copies that band
         // while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
         CUDA_OK(cudaMemsetAsync(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands, e->stream));
         CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows);
         if (rc) return rc;
+        if ((rc = enqueue_h2d_bands())) return rc;
         CUDA_OK(cudaStreamWaitEvent(e->stream_d2h, e->ev_in, 0));      // counters are zeroed before anybody waits on them
         const int gx = (e->out_w + TW - 1) / TW;
         const int bty = (e->last_grid_y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
@@ -594,8 +652,9 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
         CUDA_OK(cudaStreamSynchronize(e->stream));
     } else {
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows);
         if (rc) return rc;
+        if ((rc = enqueue_h2d_bands())) return rc;
         CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
         CUDA_OK(cudaStreamSynchronize(e->stream));
     }
@@ -629,6 +688,8 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     e->yx.release(); e->yy.release(); e->cx.release(); e->cy.release();
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream_d2h) cudaStreamDestroy(e->stream_d2h);
+    if (e->stream_h2d) cudaStreamDestroy(e->stream_h2d);
+    cudaFree(e->d_in_ready);
     cudaFree(e->d_band_done);
     if (e->stream_uv) cudaStreamDestroy(e->stream_uv);
     if (e->ev_uv) cudaEventDestroy(e->ev_uv);
