@@ -188,7 +188,7 @@ int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStre
     if (e->use_pipe) {
         // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
         const int ntiles = (int)(grid.x * grid.y);
-        raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NT, PIPE_SMEM_BYTES, s>>>(q);
+        raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NTP, PIPE_SMEM_BYTES, s>>>(q);
     } else if (e->cluster == 2 && (grid.x % 2 == 0)) {
         // pairs of horizontally neighbouring tiles form a thread-block cluster and share every filter-slice load
         cudaLaunchConfig_t cfg{};

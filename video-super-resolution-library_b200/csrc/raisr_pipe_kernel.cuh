@@ -19,9 +19,11 @@
 
 namespace raisr {
 
-constexpr int NPW = 8;                       // producer warps
-constexpr int NCW = NT / 32 - NPW;           // consumer warps
+constexpr int NTP = 640;                     // threads per CTA of the pipelined kernel: 8 producer + 12 consumer warps
+constexpr int NPW = 8;                       // producer warps (2 warpgroups)
+constexpr int NCW = NTP / 32 - NPW;          // consumer warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
+constexpr int PROD_REGS = 56, CONS_REGS = 120;   // setmaxnreg targets: 256*56 + 384*120 <= 640*96 registers of the CTA
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
 static_assert(RBP * QW == NPT && RING >= RBP + 12 && (RING & (RING - 1)) == 0, "producer geometry");
@@ -66,7 +68,7 @@ __device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
 }
 
 template <typename PixT, int PT, int UPS>
-__global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams p)
+__global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sS = reinterpret_cast<float *>(smem_raw + POFF_S);
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams
 
     if (tid < NPT) {
         // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));   // hand registers to the consumer warpgroups
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_pipe_kernel(const PassParams
         }
     } else {
         // =========================== consumer: filter + blend of tile i ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
         const int ct = tid - NPT;
         const int lane = ct & 31, cwarp = ct >> 5;
         const int g = lane >> 3, q = lane & 7;
