@@ -19,11 +19,11 @@
 
 namespace raisr {
 
-constexpr int NTP = 640;                     // threads per CTA of the pipelined kernel: 8 producer + 12 consumer warps
+constexpr int NTP = 768;                     // threads per CTA of the pipelined kernel: 8 producer + 16 consumer warps
 constexpr int NPW = 8;                       // producer warps (2 warpgroups)
 constexpr int NCW = NTP / 32 - NPW;          // consumer warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
-constexpr int PROD_REGS = 56, CONS_REGS = 120;   // setmaxnreg targets: 256*56 + 384*120 <= 640*96 registers of the CTA
+constexpr int PROD_REGS = 48, CONS_REGS = 96;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
 static_assert(RBP * QW == NPT && RING >= RBP + 12 && (RING & (RING - 1)) == 0, "producer geometry");
@@ -41,6 +41,15 @@ constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 5 * 8;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// mbarrier wait for hand-offs that may take a long time: back off so that the spinning warps do not eat issue slots
+__device__ __forceinline__ void mbar_wait_backoff(void *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done) __nanosleep(200);
+    } while (!done);
+}
 __device__ __forceinline__ void mbar_arrive(void *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
-            mbar_wait(mempty0 + buf, (unsigned)(((iter >> 1) & 1) ^ 1));     // the consumer is done with this bucket tile
+            mbar_wait_backoff(mempty0 + buf, (unsigned)(((iter >> 1) & 1) ^ 1));     // the consumer is done with this bucket tile
             const bool cols_hashed = (x0 - 1 + HW > 6) && (x0 - 1 < p.c_end);
             // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk h0 needs rows h0 .. h0+RBP+11
             for (int idx = tid; idx < (RBP + 10) * SW; idx += NPT) {         // rows 0 .. RBP+9 up front (the chunk loop adds two more)
@@ -115,9 +124,31 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             for (int h0 = 0; h0 < hh; h0 += RBP) {
                 const int rfirst = y0 - 1 + h0;
                 // two new ring rows: s = h0+RBP+10, h0+RBP+11
-                for (int idx = tid; idx < RBP * SW; idx += NPT) {
-                    const int s = h0 + RBP + 10 + idx / SW, sx = idx % SW;
-                    sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                if (UPS == 1) {
+                    // s even <-> frame row Y = y0-7+s odd = 2j+1 and s+1 <-> Y+1 = 2j+2: both interpolate low-res rows (j, j+1) with
+                    // weights (3,1) and (1,3); likewise columns sx even / sx+1.  One thread = one 2x2 block from 4 low-res samples.
+                    if (tid < SW / 2) {
+                        const int s = h0 + RBP + 10, sx = 2 * tid;
+                        const int Y = y0 - 7 + s, X = x0 - 7 + sx;                    // both odd
+                        const int j = Y >> 1, i = X >> 1;
+                        const int ya = min(max(j, 0), p.up_src_h - 1), yb = min(max(j + 1, 0), p.up_src_h - 1);
+                        const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
+                        const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
+                        const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
+                        const float a = (float)ra[xa], b = (float)ra[xb], c = (float)rb[xa], d = (float)rb[xb];
+                        const float t0 = ffma(3.0f, a, c), t1 = ffma(3.0f, b, d);     // row Y   : 3*row(j) + row(j+1)
+                        const float u0 = ffma(3.0f, c, a), u1 = ffma(3.0f, d, b);     // row Y+1 : row(j) + 3*row(j+1)
+                        float *r0 = sRing + (s & (RING - 1)) * SP + sx, *r1 = sRing + ((s + 1) & (RING - 1)) * SP + sx;
+                        r0[0] = floorf(fmul(fadd(ffma(3.0f, t0, t1), 8.0f), 0.0625f));   // col X   : 3*col(i) + col(i+1)
+                        r0[1] = floorf(fmul(fadd(ffma(3.0f, t1, t0), 8.0f), 0.0625f));   // col X+1 : col(i) + 3*col(i+1)
+                        r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
+                        r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
+                    }
+                } else {
+                    for (int idx = tid; idx < RBP * SW; idx += NPT) {
+                        const int s = h0 + RBP + 10 + idx / SW, sx = idx % SW;
+                        sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                    }
                 }
                 group_sync(1, NPT);
                 const bool any_hashed = cols_hashed && (rfirst + RBP > 6) && (rfirst < H - 6);
@@ -266,7 +297,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int h = idx / HW, j = idx - h * HW;
                 sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
             }
-            mbar_wait(mfull0 + buf, (unsigned)((iter >> 1) & 1));             // buckets of this tile are ready
+            mbar_wait_backoff(mfull0 + buf, (unsigned)((iter >> 1) & 1));     // buckets of this tile are ready
             group_sync(2, NCT);
 
             // ---- D: 121-tap filter, one pixel type at a time ----
