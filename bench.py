@@ -337,7 +337,7 @@ def main():
                     "d2h_bytes_per_step": world * FRAMES_PER_STEP * (OUT_W * OUT_H + 2 * (OUT_W // 2) * (OUT_H // 2))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "raisr_pass_kernel<uint8_t>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "raisr_pass_kernel<uint8_t>" if os.environ.get("RAISR_CUDA_KERNEL") == "tile" else "raisr_pass_pipe_kernel<uint8_t,4,1>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_Y,
                          "note": "compute-bound stencil: fp32 issue + shared-memory gather, see DESIGN.md"},

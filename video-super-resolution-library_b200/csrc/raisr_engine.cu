@@ -125,7 +125,7 @@ struct raisr_cuda_engine {
     int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
     int zero_copy = 2;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (measured +4 % end to end); RAISR_CUDA_ZERO_COPY overrides
     int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
-    bool use_pipe = false;          // RAISR_CUDA_KERNEL=pipe selects the warp-specialised persistent kernel (measured: no faster)
+    bool use_pipe = true;           // persistent warp-specialised kernel (0.74 ms per 4K frame); RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (0.85 ms)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
     // geometry
@@ -412,7 +412,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
     if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
     if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
-    if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "pipe") == 0;
+    if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
         // contiguous bytes per step: tap k = 16m + j  ->  position (m/2)*32 + (j/2)*4 + (m%2)*2 + (j%2)   (see dot8())

@@ -65,7 +65,7 @@ struct PassParams {
 };
 
 // Gaussian weights, folded: c_gw[i][m] = w[i][m] = w[i][10-m], m = 0..5   (Raisr_globals.h:208-264)
-__constant__ float c_gw[11][6];
+__constant__ __align__(16) float c_gw[11][6];
 
 // ---- tile geometry -------------------------------------------------------------------------------
 constexpr int NT = 512;          // threads per CTA (one CTA per SM: the filter slice alone is 110 KB)

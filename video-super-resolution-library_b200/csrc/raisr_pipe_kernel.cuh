@@ -6,14 +6,15 @@
 // by the shared-memory pipe with the FMA pipe idle.  Here one CTA per SM loops over tiles with two warp groups:
 //   producer warps : tile i+1 -- stream the upscaled rows through a 16-row ring, column chains, buckets  -> bucket tile[(i+1)&1]
 //   consumer warps : tile i   -- S tile, per-type filter slices (cp.async.bulk), 8-lane filter, blend, store
-// so the FMA-bound and the LSU-bound work of neighbouring tiles overlap on the same SM.  The hand-off is a pair of
-// mbarrier-guarded bucket tiles (full/empty), group-local synchronisation uses named barriers.
+// so the FMA-bound and the LSU-bound work of neighbouring tiles overlap on the same SM.  The hand-off is a pair of bucket
+// tiles guarded by hardware named barriers (bar.arrive / bar.sync, full and empty per tile buffer: the waiting side blocks
+// without consuming issue slots), group-local synchronisation uses two more named barriers.
 //
-// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite) but NOT faster on B200 (0.85 ms vs 0.84 ms per
-// 4K frame with 8+8 warps, 0.98 ms with 4+12): with 128 registers x 512 threads the register file caps the CTA at 16
-// warps, and halving the warps of the filter stage halves the loads it keeps in flight -- it turns from shared-memory
-// bandwidth bound into latency bound and loses what the overlap gains.  Kept selectable (RAISR_CUDA_KERNEL=pipe) as the
-// measured alternative; the default is the phase-sequential kernel.
+// Register file: the CTA is launched with 80 registers per thread; the producer warpgroups drop to 48 and the consumer
+// warpgroups rise to 96 (setmaxnreg).  Producer: the upscaled rows of the next chunk are fetched from global memory before
+// stage B and stored into free ring slots after stage C (latency hidden); stage B uses packed FMUL2/FFMA2.
+//
+// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite), and the default: 8 producer + 16 consumer warps.
 #pragma once
 #include "raisr_kernels.cuh"
 
@@ -23,10 +24,10 @@ constexpr int NTP = 768;                     // threads per CTA of the pipelined
 constexpr int NPW = 8;                       // producer warps (2 warpgroups)
 constexpr int NCW = NTP / 32 - NPW;          // consumer warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
-constexpr int PROD_REGS = 48, CONS_REGS = 96;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
+constexpr int PROD_REGS = 56, CONS_REGS = 88;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
-static_assert(RBP * QW == NPT && RING >= RBP + 12 && (RING & (RING - 1)) == 0, "producer geometry");
+static_assert(RBP * QW == NPT && RING >= 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP % 2 == 0 && SW % 2 == 0, "producer geometry");
 
 constexpr size_t POFF_S = 0;
 constexpr size_t POFF_HR = POFF_S + sizeof(float) * SH * SP;
@@ -36,24 +37,23 @@ constexpr size_t POFF_HASH2 = POFF_HASH + 2 * (size_t)HH * HP;             // 2 
 constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)HH * OVW + 15) & ~(size_t)15;
 constexpr size_t POFF_RING = POFF_LUT + 256 * sizeof(uint2);
 constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;
-constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * RBP * 18 * QW;       // slice, full[2], empty[2]
-constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 5 * 8;
+constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * RBP * 18 * QW;       // filter-slice mbarrier
+constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-// mbarrier wait for hand-offs that may take a long time: back off so that the spinning warps do not eat issue slots
-__device__ __forceinline__ void mbar_wait_backoff(void *bar, unsigned parity)
-{
-    unsigned done;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!done) __nanosleep(200);
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(void *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+// producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
+// mbarrier spin), the signalling side does not wait (bar.arrive).  count = all threads of both sides.
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5;   // FULL/EMPTY + bucket tile index (0/1)
+
+// Packed fp32 pairs (sm_100 FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, i.e. the same roundings as
+// two scalar instructions at half the issue slots.  Stage B keeps its chains for weight columns (m, m+1) in one 64-bit pair.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // One sample of the upscaled plane for the producer's ring (out-of-frame coordinates are clamped: such samples only
 // feed pixels that are never hashed).
@@ -87,26 +87,56 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
     float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
     float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
     unsigned long long *mbars = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
-    unsigned long long *mslice = mbars, *mfull0 = mbars + 1, *mempty0 = mbars + 3;
+    unsigned long long *mslice = mbars;
 
-    const int tid = threadIdx.x;
+    const int tid0 = threadIdx.x;
     const int th = p.tile_h, hh = th + 2;
     const int W = p.W, H = p.H;
     const int gx = (W + TW - 1) / TW;
     const int ntiles = gx * ((p.row1 - p.row0 + th - 1) / th);
 
-    if (p.numerics != 0 && tid < 256) sLut[tid] = (tid < 128) ? p.lut_rsqrt14[tid] : p.lut_rcp14[tid - 128];
-    if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(mbars + i, 1);
+    if (p.numerics != 0 && tid0 < 256) sLut[tid0] = (tid0 < 128) ? p.lut_rsqrt14[tid0] : p.lut_rcp14[tid0 - 128];
+    if (tid0 == 0) {
+        mbar_init(mslice, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
 
-    if (tid < NPT) {
+    // warps [0, NCW) are consumers, warps [NCW, NCW + NPW) producers (PIPE_PROD_FIRST: the other way round)
+#ifdef PIPE_PROD_FIRST
+    const bool is_prod = tid0 < NPT;
+    const int tid = tid0, ct = tid0 - NPT;
+#else
+    const bool is_prod = tid0 >= NCT;
+    const int tid = tid0 - NCT, ct = tid0;
+#endif
+    if (is_prod) {
         // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));   // hand registers to the consumer warpgroups
+        // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
+        // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
+        // columns sx = 2t, 2t+1.  Split into load and store so that the global-memory latency hides behind stage B.
+        auto load_block = [&](int s, int t, int y0, int x0, unsigned &ab, unsigned &cd) {   // raw samples, two per register
+            const int j = (y0 - 7 + s) >> 1, i = (x0 - 7 + 2 * t) >> 1;
+            const int ya = min(max(j, 0), p.up_src_h - 1), yb = min(max(j + 1, 0), p.up_src_h - 1);
+            const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
+            const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
+            const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
+            ab = (unsigned)ra[xa] | ((unsigned)ra[xb] << 16);
+            cd = (unsigned)rb[xa] | ((unsigned)rb[xb] << 16);
+        };
+        auto store_block = [&](int s, int t, unsigned ab, unsigned cd) {
+            const float a = (float)(ab & 0xffffu), b = (float)(ab >> 16), c = (float)(cd & 0xffffu), d = (float)(cd >> 16);
+            const float t0 = ffma(3.0f, a, c), t1 = ffma(3.0f, b, d);     // row Y   : 3*row(j) + row(j+1)
+            const float u0 = ffma(3.0f, c, a), u1 = ffma(3.0f, d, b);     // row Y+1 : row(j) + 3*row(j+1)
+            float *r0 = sRing + (s & (RING - 1)) * SP + 2 * t, *r1 = sRing + ((s + 1) & (RING - 1)) * SP + 2 * t;
+            r0[0] = floorf(fmul(fadd(ffma(3.0f, t0, t1), 8.0f), 0.0625f));   // col X   : 3*col(i) + col(i+1)
+            r0[1] = floorf(fmul(fadd(ffma(3.0f, t1, t0), 8.0f), 0.0625f));   // col X+1 : col(i) + 3*col(i+1)
+            r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
+            r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
+        };
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
@@ -114,53 +144,43 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
-            mbar_wait_backoff(mempty0 + buf, (unsigned)(((iter >> 1) & 1) ^ 1));     // the consumer is done with this bucket tile
+            if (iter >= 2) group_sync(BAR_EMPTY + buf, NTP);                 // the consumer is done with this bucket tile (tile i-2)
             const bool cols_hashed = (x0 - 1 + HW > 6) && (x0 - 1 < p.c_end);
-            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk h0 needs rows h0 .. h0+RBP+11
-            for (int idx = tid; idx < (RBP + 10) * SW; idx += NPT) {         // rows 0 .. RBP+9 up front (the chunk loop adds two more)
-                const int s = idx / SW, sx = idx - s * SW;
-                sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk h0 reads rows h0 .. h0+RBP+11.
+            // Rows 0 .. RBP+11 up front; every chunk then fetches the RBP rows of the NEXT chunk (slots the current one does not read).
+            if (UPS == 1) {
+                for (int idx = tid; idx < ((RBP + 12) / 2) * (SW / 2); idx += NPT) {
+                    const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
+                    unsigned ab, cd;
+                    load_block(2 * sp2, t, y0, x0, ab, cd);
+                    store_block(2 * sp2, t, ab, cd);
+                }
+            } else {
+                for (int idx = tid; idx < (RBP + 12) * SW; idx += NPT) {
+                    const int s = idx / SW, sx = idx - s * SW;
+                    sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                }
             }
             for (int h0 = 0; h0 < hh; h0 += RBP) {
                 const int rfirst = y0 - 1 + h0;
-                // two new ring rows: s = h0+RBP+10, h0+RBP+11
-                if (UPS == 1) {
-                    // s even <-> frame row Y = y0-7+s odd = 2j+1 and s+1 <-> Y+1 = 2j+2: both interpolate low-res rows (j, j+1) with
-                    // weights (3,1) and (1,3); likewise columns sx even / sx+1.  One thread = one 2x2 block from 4 low-res samples.
-                    if (tid < SW / 2) {
-                        const int s = h0 + RBP + 10, sx = 2 * tid;
-                        const int Y = y0 - 7 + s, X = x0 - 7 + sx;                    // both odd
-                        const int j = Y >> 1, i = X >> 1;
-                        const int ya = min(max(j, 0), p.up_src_h - 1), yb = min(max(j + 1, 0), p.up_src_h - 1);
-                        const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
-                        const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
-                        const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
-                        const float a = (float)ra[xa], b = (float)ra[xb], c = (float)rb[xa], d = (float)rb[xb];
-                        const float t0 = ffma(3.0f, a, c), t1 = ffma(3.0f, b, d);     // row Y   : 3*row(j) + row(j+1)
-                        const float u0 = ffma(3.0f, c, a), u1 = ffma(3.0f, d, b);     // row Y+1 : row(j) + 3*row(j+1)
-                        float *r0 = sRing + (s & (RING - 1)) * SP + sx, *r1 = sRing + ((s + 1) & (RING - 1)) * SP + sx;
-                        r0[0] = floorf(fmul(fadd(ffma(3.0f, t0, t1), 8.0f), 0.0625f));   // col X   : 3*col(i) + col(i+1)
-                        r0[1] = floorf(fmul(fadd(ffma(3.0f, t1, t0), 8.0f), 0.0625f));   // col X+1 : col(i) + 3*col(i+1)
-                        r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
-                        r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
-                    }
-                } else {
-                    for (int idx = tid; idx < RBP * SW; idx += NPT) {
-                        const int s = h0 + RBP + 10 + idx / SW, sx = idx % SW;
-                        sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
-                    }
-                }
-                group_sync(1, NPT);
+                const bool more = h0 + RBP < hh;
+                unsigned pab = 0u, pcd = 0u;
+                if (UPS == 1 && more && tid < SW / 2) load_block(h0 + RBP + 12, tid, y0, x0, pab, pcd);
+                group_sync(BAR_PROD, NPT);                                   // ring rows of this chunk are in place; C(previous chunk) is done with sQ
+#ifdef PIPE_DBG_SKIP_BC
+                const bool any_hashed = false;
+#else
                 const bool any_hashed = cols_hashed && (rfirst + RBP > 6) && (rfirst < H - 6);
+#endif
                 if (any_hashed) {
                     // ---- B: column chains, one position per thread (gradients straight from the ring) ----
                     const int rl = tid / QW, q = tid - rl * QW;
                     const int r = rfirst + rl;
                     if (r >= 6 && r < H - 6 && h0 + rl < hh) {
                         const int s0 = h0 + rl;                                  // S row above the first gradient row
-                        float acc[6][3];
+                        f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
 #pragma unroll
-                        for (int m = 0; m < 6; ++m) acc[m][0] = acc[m][1] = acc[m][2] = 0.0f;
+                        for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
                         float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
                         const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
                         float vcur = row[1];
@@ -170,23 +190,29 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                             const float vnext = nrow[1];
                             const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
                             const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
+                            const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
 #pragma unroll
-                            for (int m = 0; m < 6; ++m) {
-                                const float w = c_gw[i][m];
-                                const float px = fmul(gxv, w), py = fmul(gyv, w);
-                                acc[m][0] = ffma(px, gxv, acc[m][0]);
-                                acc[m][1] = ffma(px, gyv, acc[m][1]);
-                                acc[m][2] = ffma(py, gyv, acc[m][2]);
+                            for (int mm = 0; mm < 3; ++mm) {
+                                const f32x2 w2 = pack2(c_gw[i][2 * mm], c_gw[i][2 * mm + 1]);
+                                const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
+                                acc[mm][0] = fma2(px, gx2, acc[mm][0]);
+                                acc[mm][1] = fma2(px, gy2, acc[mm][1]);
+                                acc[mm][2] = fma2(py, gy2, acc[mm][2]);
                             }
                             vprev = vcur; vcur = vnext; row = nrow;
                         }
                         float *qd = sQ + (rl * 18) * QW + q;
 #pragma unroll
-                        for (int m = 0; m < 6; ++m)
+                        for (int mm = 0; mm < 3; ++mm)
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) qd[(m * 3 + k) * QW] = acc[m][k];
+                            for (int k = 0; k < 3; ++k) {
+                                float lo, hi;
+                                unpack2(acc[mm][k], lo, hi);
+                                qd[(2 * mm * 3 + k) * QW] = lo;
+                                qd[((2 * mm + 1) * 3 + k) * QW] = hi;
+                            }
                     }
-                    group_sync(1, NPT);
+                    group_sync(BAR_PROD, NPT);
                 }
                 // ---- C: bucket, one pixel per thread ----
                 {
@@ -223,15 +249,23 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                         if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
                     }
                 }
-                // the next chunk's ring fill overwrites rows B no longer reads; its barrier also orders C(this) before B(next)
+                // ring rows of the next chunk (slots this chunk's stage B does not read; the barrier at the top of the next chunk publishes them)
+                if (more) {
+                    if (UPS == 1) {
+                        if (tid < SW / 2) store_block(h0 + RBP + 12, tid, pab, pcd);
+                    } else {
+                        for (int idx = tid; idx < RBP * SW; idx += NPT) {
+                            const int s = h0 + RBP + 12 + idx / SW, sx = idx % SW;
+                            sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                        }
+                    }
+                }
             }
-            group_sync(1, NPT);
-            if (tid == 0) mbar_arrive(mfull0 + buf);
+            named_arrive(BAR_FULL + buf, NTP);                               // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
         }
     } else {
         // =========================== consumer: filter + blend of tile i ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-        const int ct = tid - NPT;
         const int lane = ct & 31, cwarp = ct >> 5;
         const int g = lane >> 3, q = lane & 7;
         constexpr int JS = (PT == 4) ? 2 : 1;
@@ -269,7 +303,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
                     sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
                 }
-                group_sync(2, NCT);
+                group_sync(BAR_CONS, NCT);
                 for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
                     const int bi = idx / (LRW - 1) + 1, bj = idx - (bi - 1) * (LRW - 1) + 1;
                     const float *l = sL + bi * LRP + bj;
@@ -291,18 +325,21 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     sS[sy * SP + sx] = v;
                 }
             }
-            group_sync(2, NCT);
+            group_sync(BAR_CONS, NCT);
             // HR := S; the filter phase overwrites accepted pixels
             for (int idx = ct; idx < hh * HW; idx += NCT) {
                 const int h = idx / HW, j = idx - h * HW;
                 sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
             }
-            mbar_wait_backoff(mfull0 + buf, (unsigned)((iter >> 1) & 1));     // buckets of this tile are ready
-            group_sync(2, NCT);
+            group_sync(BAR_FULL + buf, NTP);                                  // buckets of this tile are ready (also publishes S / HR to the group)
 
             // ---- D: 121-tap filter, one pixel type at a time ----
             const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
+#ifdef PIPE_DBG_SKIP_D
+            for (int t = 0; t < 0; ++t) {
+#else
             for (int t = 0; t < PT; ++t) {
+#endif
                 if (ct == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(mslice, (unsigned)slice_bytes);
@@ -354,19 +391,28 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                         if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
                     }
                 };
-                for (int it = cwarp; it < nrows * NBLK; it += NCW) {
+                // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
+                // single pixel groups over all warps so that no warp waits a whole item at the barrier
+                const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
+                for (int it = cwarp; it < nfull; it += NCW) {
                     const int ri = it / NBLK, bi = it - ri * NBLK;
                     const int h = hfirst + ri * JS;
                     const int jb = jfirst + (bi * 4 * U + g) * JS;
                     if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
                     else block(std::integral_constant<int, ULAST>{}, h, jb);
                 }
-                group_sync(2, NCT);
+                for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
+                    const int it = nfull + rq / U, u = rq - (rq / U) * U;
+                    const int ri = it / NBLK, bi = it - ri * NBLK;
+                    if (bi == NBLK - 1 && u >= ULAST) continue;
+                    block(std::integral_constant<int, 1>{}, hfirst + ri * JS, jfirst + (bi * 4 * U + 4 * u + g) * JS);
+                }
+                group_sync(BAR_CONS, NCT);
             }
             // ---- E: blend + store ----
             stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
-            group_sync(2, NCT);                                               // S / HR are rewritten by the next tile's stage A
-            if (ct == 0) mbar_arrive(mempty0 + buf);                          // bucket tile may be refilled (tile i+2)
+            group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
+            if (tile + 2 * (int)gridDim.x < ntiles) named_arrive(BAR_EMPTY + buf, NTP);   // bucket tile may be refilled (tile i+2)
             if (p.band_done && ct == 0) {
                 __threadfence();
                 atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
