@@ -212,10 +212,11 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
     // tile height: the largest even th <= TH_MAX whose tile count still fits the same number of waves (one CTA per SM)
     PassParams q = p;
     const int rows = p.row1 - p.row0, gx = (p.W + TW - 1) / TW;
-    int ny = (rows + TH_MAX - 1) / TH_MAX;
+    const int thmax = e->use_pipe ? PTH_MAX : TH_MAX;
+    int ny = (rows + thmax - 1) / thmax;
     const int waves = (gx * ny + e->num_sms - 1) / e->num_sms;
     while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && 2 * (ny + 1) <= rows) ++ny;
-    q.tile_h = std::min(TH_MAX, (((rows + ny - 1) / ny) + 1) & ~1);
+    q.tile_h = std::min(thmax, (((rows + ny - 1) / ny) + 1) & ~1);
     const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
     e->last_grid_y = (int)grid.y; e->last_tile_h = q.tile_h;
     if (q.band_done) q.band_tiles_y = ((int)grid.y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;

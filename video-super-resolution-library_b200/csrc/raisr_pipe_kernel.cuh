@@ -24,22 +24,26 @@ constexpr int NTP = 768;                     // threads per CTA of the pipelined
 constexpr int NPW = 8;                       // producer warps (2 warpgroups)
 constexpr int NCW = NTP / 32 - NPW;          // consumer warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
-constexpr int PROD_REGS = 56, CONS_REGS = 88;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
+constexpr int PROD_REGS = 64, CONS_REGS = 88;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
-static_assert(RBP * QW == NPT && RING >= 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP % 2 == 0 && SW % 2 == 0, "producer geometry");
+static_assert(RBP * QW == NPT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
 
+constexpr int PTH_MAX = 46;                  // output tile height of the pipelined kernel (smaller than TH_MAX: the chain buffer is double-buffered)
+constexpr int PSH = PTH_MAX + 14, PHH = PTH_MAX + 2;
+constexpr int QCHUNK = RBP * 18 * QW;        // floats of one chunk's column chains
 constexpr size_t POFF_S = 0;
-constexpr size_t POFF_HR = POFF_S + sizeof(float) * SH * SP;
-constexpr size_t POFF_F = (POFF_HR + sizeof(float) * HH * HP + 127) & ~(size_t)127;
+constexpr size_t POFF_HR = POFF_S + sizeof(float) * PSH * SP;
+constexpr size_t POFF_F = (POFF_HR + sizeof(float) * PHH * HP + 127) & ~(size_t)127;
 constexpr size_t POFF_HASH = POFF_F + sizeof(float) * SLICE_FLOATS;        // 2 bucket tiles
-constexpr size_t POFF_HASH2 = POFF_HASH + 2 * (size_t)HH * HP;             // 2 overlap-column tiles
-constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)HH * OVW + 15) & ~(size_t)15;
+constexpr size_t POFF_HASH2 = POFF_HASH + 2 * (size_t)PHH * HP;            // 2 overlap-column tiles
+constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)PHH * OVW + 15) & ~(size_t)15;
 constexpr size_t POFF_RING = POFF_LUT + 256 * sizeof(uint2);
-constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;
-constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * RBP * 18 * QW;       // filter-slice mbarrier
+constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;           // 2 chunks of column chains
+constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * 2 * QCHUNK;          // filter-slice mbarrier
 constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(float) * (((PTH_MAX + 14) / 2 + 1) * LRP) <= sizeof(float) * SLICE_FLOATS, "low-res staging fits in the slice buffer");
 
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
@@ -54,6 +58,17 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b
 __device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Shared-memory loads by 32-bit shared address + compile-time byte offset.  The filter stage composes its addresses as
+// (per-lane constant) + (warp-uniform tile/row part) + immediate, which maps onto the LDS [R + UR + imm] addressing mode: no
+// per-load address arithmetic.  volatile: never merged or hoisted across the barriers that order them with the stores.
+template <int IMM> __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(IMM)); return v; }
+template <int IMM> __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(IMM)); return v; }
+template <int IMM> __device__ __forceinline__ void lds_f32x2x2(unsigned a, f32x2 &lo, f32x2 &hi)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(lo), "=l"(hi) : "r"(a), "n"(IMM));
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 // One sample of the upscaled plane for the producer's ring (out-of-frame coordinates are clamped: such samples only
 // feed pixels that are never hashed).
@@ -96,6 +111,8 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
     const int ntiles = gx * ((p.row1 - p.row0 + th - 1) / th);
 
     if (p.numerics != 0 && tid0 < 256) sLut[tid0] = (tid0 < 128) ? p.lut_rsqrt14[tid0] : p.lut_rcp14[tid0 - 128];
+    for (int i = tid0; i < 2 * PHH * (HP - HW); i += NTP)                 // pad columns of both bucket tiles: "not hashed"
+        smem_raw[POFF_HASH + (size_t)(i / (HP - HW)) * HP + HW + i % (HP - HW)] = 255;
     if (tid0 == 0) {
         mbar_init(mslice, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,122 +157,114 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
-            unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * HH * HP;
-            unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
+            unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
+            unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
             if (iter >= 2) group_sync(BAR_EMPTY + buf, NTP);                 // the consumer is done with this bucket tile (tile i-2)
-            const bool cols_hashed = (x0 - 1 + HW > 6) && (x0 - 1 < p.c_end);
-            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk h0 reads rows h0 .. h0+RBP+11.
-            // Rows 0 .. RBP+11 up front; every chunk then fetches the RBP rows of the NEXT chunk (slots the current one does not read).
+            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1) reads
+            // rows 2k .. 2k+13.  Rows 0 .. 15 (chunks 0 and 1) up front; iteration k fetches the two rows of chunk k+2.
             if (UPS == 1) {
-                for (int idx = tid; idx < ((RBP + 12) / 2) * (SW / 2); idx += NPT) {
+                for (int idx = tid; idx < (RING / 2) * (SW / 2); idx += NPT) {
                     const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
                     unsigned ab, cd;
                     load_block(2 * sp2, t, y0, x0, ab, cd);
                     store_block(2 * sp2, t, ab, cd);
                 }
             } else {
-                for (int idx = tid; idx < (RBP + 12) * SW; idx += NPT) {
+                for (int idx = tid; idx < RING * SW; idx += NPT) {
                     const int s = idx / SW, sx = idx - s * SW;
-                    sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                    sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
                 }
             }
-            for (int h0 = 0; h0 < hh; h0 += RBP) {
-                const int rfirst = y0 - 1 + h0;
-                const bool more = h0 + RBP < hh;
+            const int rl = tid / QW, q = tid - rl * QW;          // this thread's row of a chunk and chain column / pixel column
+            // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
+            // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
+            auto stage_B = [&](int kb) {
+                const int s0 = RBP * kb + rl;                            // S row above the first gradient row
+                f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
+                float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
+                const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
+                float vcur = row[1];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
+                    const float vnext = nrow[1];
+                    const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
+                    const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
+                    const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
+#pragma unroll
+                    for (int mm = 0; mm < 3; ++mm) {
+                        const f32x2 w2 = pack2(c_gw[i][2 * mm], c_gw[i][2 * mm + 1]);
+                        const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
+                        acc[mm][0] = fma2(px, gx2, acc[mm][0]);
+                        acc[mm][1] = fma2(px, gy2, acc[mm][1]);
+                        acc[mm][2] = fma2(py, gy2, acc[mm][2]);
+                    }
+                    vprev = vcur; vcur = vnext; row = nrow;
+                }
+                float *qd = sQ + (kb & 1) * QCHUNK + (rl * 18) * QW + q;
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float lo, hi;
+                        unpack2(acc[mm][k], lo, hi);
+                        qd[(2 * mm * 3 + k) * QW] = lo;
+                        qd[((2 * mm + 1) * 3 + k) * QW] = hi;
+                    }
+            };
+            // ---- C: bucket of chunk kc, one pixel per thread <- sQ[kc & 1].  The 16-wide hash runs unconditionally (garbage in,
+            // nothing stored, for threads without a hashed pixel); only the row-tail columns take the 8-wide branch.
+            auto stage_C = [&](int kc) {
+                const int h = RBP * kc + rl;
+                const int j = min(q, HW - 1);
+                const int r = y0 - 1 + h, c = x0 - 1 + j;
+                float g[3];
+                const float *qs = sQ + (kc & 1) * QCHUNK + (rl * 18) * QW + j;
+#pragma unroll
+                for (int k3 = 0; k3 < 3; ++k3) {
+                    float lane[11];
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        const int m = k < 6 ? k : 10 - k;
+                        lane[k] = qs[(m * 3 + k3) * QW + k];
+                    }
+                    g[k3] = tree_sum(lane);
+                }
+                const bool hashed = r >= 6 && r < H - 6 && c >= 6 && c < p.c_end;
+                int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
+                if (hashed && c >= p.tail_start) {
+                    const int h8 = hash_bucket<false>(hc, g[0], g[1], g[2]);
+                    if (c < p.ov_end && hv != h8) hv2 = hv;         // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
+                    hv = h8;
+                }
+                if (!hashed) hv = 255;
+                if (q < HW && h < hh) {
+                    if (p.hash_out && hashed && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
+                    sHash[h * HP + j] = (unsigned char)hv;
+                    if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
+                }
+            };
+            const int nchunks = hh / RBP;
+            group_sync(BAR_PROD, NPT);                                       // ring rows 0 .. 15 are in place
+            stage_B(0);
+            for (int k = 0; k < nchunks; ++k) {
+                // fetch the ring rows of chunk k+2 (rows 2k+16, 2k+17: the slots of rows 2k, 2k+1, last read by B(k))
+                const bool more = k + 2 < nchunks;
                 unsigned pab = 0u, pcd = 0u;
-                if (UPS == 1 && more && tid < SW / 2) load_block(h0 + RBP + 12, tid, y0, x0, pab, pcd);
-                group_sync(BAR_PROD, NPT);                                   // ring rows of this chunk are in place; C(previous chunk) is done with sQ
-#ifdef PIPE_DBG_SKIP_BC
-                const bool any_hashed = false;
-#else
-                const bool any_hashed = cols_hashed && (rfirst + RBP > 6) && (rfirst < H - 6);
-#endif
-                if (any_hashed) {
-                    // ---- B: column chains, one position per thread (gradients straight from the ring) ----
-                    const int rl = tid / QW, q = tid - rl * QW;
-                    const int r = rfirst + rl;
-                    if (r >= 6 && r < H - 6 && h0 + rl < hh) {
-                        const int s0 = h0 + rl;                                  // S row above the first gradient row
-                        f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
-                        float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
-                        const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
-                        float vcur = row[1];
-#pragma unroll
-                        for (int i = 0; i < 11; ++i) {
-                            const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
-                            const float vnext = nrow[1];
-                            const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
-                            const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
-                            const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
-#pragma unroll
-                            for (int mm = 0; mm < 3; ++mm) {
-                                const f32x2 w2 = pack2(c_gw[i][2 * mm], c_gw[i][2 * mm + 1]);
-                                const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
-                                acc[mm][0] = fma2(px, gx2, acc[mm][0]);
-                                acc[mm][1] = fma2(px, gy2, acc[mm][1]);
-                                acc[mm][2] = fma2(py, gy2, acc[mm][2]);
-                            }
-                            vprev = vcur; vcur = vnext; row = nrow;
-                        }
-                        float *qd = sQ + (rl * 18) * QW + q;
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm)
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                float lo, hi;
-                                unpack2(acc[mm][k], lo, hi);
-                                qd[(2 * mm * 3 + k) * QW] = lo;
-                                qd[((2 * mm + 1) * 3 + k) * QW] = hi;
-                            }
-                    }
-                    group_sync(BAR_PROD, NPT);
-                }
-                // ---- C: bucket, one pixel per thread ----
-                {
-                    const int rl = tid / QW, j = tid - rl * QW;
-                    const int h = h0 + rl;
-                    if (j < HW && h < hh) {
-                        const int r = rfirst + rl, c = x0 - 1 + j;
-                        int hv = 255, hv2 = 255;
-                        if (any_hashed && r >= 6 && r < H - 6 && c >= 6 && c < p.c_end) {
-                            float g[3];
-                            const float *qs = sQ + (rl * 18) * QW + j;
-#pragma unroll
-                            for (int k3 = 0; k3 < 3; ++k3) {
-                                float lane[11];
-#pragma unroll
-                                for (int k = 0; k < 11; ++k) {
-                                    const int m = k < 6 ? k : 10 - k;
-                                    lane[k] = qs[(m * 3 + k3) * QW + k];
-                                }
-                                g[k3] = tree_sum(lane);
-                            }
-                            if (c < p.tail_start) {
-                                hv = hash_bucket<true>(hc, g[0], g[1], g[2]);
-                            } else {
-                                hv = hash_bucket<false>(hc, g[0], g[1], g[2]);
-                                if (c < p.ov_end) {
-                                    const int h16 = hash_bucket<true>(hc, g[0], g[1], g[2]);
-                                    if (h16 != hv) hv2 = h16;
-                                }
-                            }
-                            if (p.hash_out && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
-                        }
-                        sHash[h * HP + j] = (unsigned char)hv;
-                        if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
-                    }
-                }
-                // ring rows of the next chunk (slots this chunk's stage B does not read; the barrier at the top of the next chunk publishes them)
+                if (UPS == 1 && more && tid < SW / 2) load_block(RBP * k + RING, tid, y0, x0, pab, pcd);
+                group_sync(BAR_PROD, NPT);                                   // B(k) complete in sQ[k & 1]; C(k-1) done with sQ[(k+1) & 1]; ring rows of chunk k+1 published
+                if (k + 1 < nchunks) stage_B(k + 1);
+                stage_C(k);
                 if (more) {
                     if (UPS == 1) {
-                        if (tid < SW / 2) store_block(h0 + RBP + 12, tid, pab, pcd);
+                        if (tid < SW / 2) store_block(RBP * k + RING, tid, pab, pcd);
                     } else {
                         for (int idx = tid; idx < RBP * SW; idx += NPT) {
-                            const int s = h0 + RBP + 12 + idx / SW, sx = idx % SW;
+                            const int s = RBP * k + RING + idx / SW, sx = idx % SW;
                             sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
                         }
                     }
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
     } else {
         // =========================== consumer: filter + blend of tile i ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-        const int lane = ct & 31, cwarp = ct >> 5;
+        const int lane = ct & 31, cwarp = __shfl_sync(0xffffffffu, ct >> 5, 0);   // warp-uniform for the compiler too
         const int g = lane >> 3, q = lane & 7;
         constexpr int JS = (PT == 4) ? 2 : 1;
         constexpr int U = 4;
@@ -284,12 +293,23 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         const float flo = (float)p.lo, fhi = (float)p.hi;
         const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
         const float4 *sF4 = reinterpret_cast<const float4 *>(sF) + q;
+        // per-lane constant parts of the fast block's shared addresses (bytes): pixel group g, lane q of the group
+        unsigned poff[8][2];                                              // patch tap (m, e) of the group's pixel in block column 0
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                poff[m][e] = smem_u32(sS) + 4u * (unsigned)(off[m][e] + SP + 1 + g * JS);
+                asm volatile("" : "+r"(poff[m][e]));                      // keep the 16 addresses in registers (no rematerialisation per block)
+            }
+        const unsigned fbase = smem_u32(sF) + 16u * (unsigned)q;          // this lane's 16 bytes of every 128-byte filter step
+        const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
         unsigned nload = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
-            const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * HH * HP;
-            const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * HH * OVW;
+            const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
+            const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
 
@@ -391,6 +411,61 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                         if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
                     }
                 };
+                // Fast form of the block for tiles without 16/8-wide overlap columns: addresses = per-lane constant + uniform + immediate,
+                // packed FMUL2/FFMA2 for the chain pair (2q, 2q+1), and the 16 -> 1 lane tree of the 4 pixel groups folded into 8 shuffles:
+                // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
+                // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
+                const unsigned hbase = smem_u32(sHash) + (unsigned)(g * JS);
+                auto fast_block = [&](auto uu, const int h, const int jc0) {   // h, jc0 (block column 0) are warp-uniform
+                    constexpr int UU = decltype(uu)::value;
+                    const unsigned ub = 4u * (unsigned)(h * SP + jc0);
+                    const unsigned hva = hbase + (unsigned)(h * HP + jc0);
+                    unsigned hv[4], fa[4];
+                    hv[0] = lds_u8<0>(hva); hv[1] = lds_u8<4 * JS>(hva);
+                    hv[2] = (UU > 2) ? lds_u8<8 * JS>(hva) : 255u; hv[3] = (UU > 3) ? lds_u8<12 * JS>(hva) : 255u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) fa[u] = fbase + (hv[u] << 9);     // 255 (not hashed): some in-bounds garbage row, result dropped
+                    f32x2 acc[4];
+                    auto step = [&](auto nn) {
+                        constexpr int n = decltype(nn)::value;
+                        const unsigned q0 = poff[2 * n][0] + ub, q1 = poff[2 * n][1] + ub, q2 = poff[2 * n + 1][0] + ub, q3 = poff[2 * n + 1][1] + ub;
+                        auto one = [&](auto uc) {
+                            constexpr int u = decltype(uc)::value;
+                            if (u < UU) {
+                                f32x2 fxy, fzw;
+                                lds_f32x2x2<n * 128>(fa[u], fxy, fzw);
+                                const f32x2 p01 = pack2(lds_f32<16 * JS * u>(q0), lds_f32<16 * JS * u>(q1));
+                                const f32x2 p23 = pack2(lds_f32<16 * JS * u>(q2), lds_f32<16 * JS * u>(q3));
+                                acc[u] = (n == 0) ? mul2(p01, fxy) : fma2(p01, fxy, acc[u]);
+                                acc[u] = fma2(p23, fzw, acc[u]);
+                            }
+                        };
+                        one(std::integral_constant<int, 0>{}); one(std::integral_constant<int, 1>{});
+                        one(std::integral_constant<int, 2>{}); one(std::integral_constant<int, 3>{});
+                    };
+                    step(std::integral_constant<int, 0>{}); step(std::integral_constant<int, 1>{});
+                    step(std::integral_constant<int, 2>{}); step(std::integral_constant<int, 3>{});
+                    // t8: lanes q < 4 keep chain 2q and take chain 2q of lane q+4; lanes q >= 4 keep chain 2q+1 and take it from lane q-4
+                    const bool hi4 = q >= 4, b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u < UU) {
+                            float a0, a1;
+                            unpack2(acc[u], a0, a1);
+                            v[u] = fadd(hi4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi4 ? a0 : a1, 4, 8));
+                        } else v[u] = 0.0f;
+                    }
+                    // t4: lanes with q & 2 keep pixels 2,3 and send 0,1; the others keep 0,1 and send 2,3
+                    const float w0 = fadd(b1 ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2, 8));
+                    const float w1 = fadd(b1 ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2, 8));
+                    // t2: lanes with q & 1 keep the odd pixel
+                    const float x = fadd(b0 ? w1 : w0, __shfl_xor_sync(0xffffffffu, b0 ? w0 : w1, 1, 8));
+                    const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));      // t2[0] + t2[1]: pixel u = q & 3
+                    const unsigned hu = b1 ? (b0 ? hv[3] : hv[2]) : (b0 ? hv[1] : hv[0]);
+                    if (q < 4 && hu != 255u && cur > flo && cur < fhi)              // strict range test, Raisr.cpp:1192-1196
+                        sts_f32(hroff + 4u * (unsigned)(h * HP + jc0), cur);
+                };
                 // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
                 // single pixel groups over all warps so that no warp waits a whole item at the barrier
                 const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
@@ -398,7 +473,10 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     const int ri = it / NBLK, bi = it - ri * NBLK;
                     const int h = hfirst + ri * JS;
                     const int jb = jfirst + (bi * 4 * U + g) * JS;
-                    if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
+                    if (!has_ov) {
+                        if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jfirst + bi * 4 * U * JS);
+                        else fast_block(std::integral_constant<int, ULAST>{}, h, jfirst + bi * 4 * U * JS);
+                    } else if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
                     else block(std::integral_constant<int, ULAST>{}, h, jb);
                 }
                 for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
