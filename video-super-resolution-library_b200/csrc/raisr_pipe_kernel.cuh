@@ -20,14 +20,15 @@
 
 namespace raisr {
 
-constexpr int NTP = 768;                     // threads per CTA of the pipelined kernel: 8 producer + 16 consumer warps
-constexpr int NPW = 8;                       // producer warps (2 warpgroups)
-constexpr int NCW = NTP / 32 - NPW;          // consumer warps (3 warpgroups)
+constexpr int NTP = 896;                     // threads per CTA of the pipelined kernel: 16 consumer + 8 chain + 8 bucket warps
+constexpr int NPW = 16;                      // producer warps: 8 chain warps (stage B) + 8 bucket warps (stage C)
+constexpr int NCW = NTP / 32 - NPW;          // consumer warps (4 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
-constexpr int PROD_REGS = 64, CONS_REGS = 88;    // setmaxnreg targets: 256*48 + 512*96 <= 768*80 registers of the CTA
-constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NPT positions)
+constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
+constexpr int PROD_REGS = 48, CONS_REGS = 104;    // setmaxnreg targets: 512*40 + 512*88 == 1024*64 registers of the CTA
+constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
-static_assert(RBP * QW == NPT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
+static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
 
 constexpr int PTH_MAX = 46;                  // output tile height of the pipelined kernel (smaller than TH_MAX: the chain buffer is double-buffered)
 constexpr int PSH = PTH_MAX + 14, PHH = PTH_MAX + 2;
@@ -154,6 +155,8 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
             r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
         };
+        const bool chain_warp = tid < NBT;                                   // sub-role: stage B (column chains) or stage C (buckets)
+        const int lt = tid & (NBT - 1);
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
@@ -164,20 +167,22 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             if (iter >= 2) group_sync(BAR_EMPTY + buf, NTP);                 // the consumer is done with this bucket tile (tile i-2)
             // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1) reads
             // rows 2k .. 2k+13.  Rows 0 .. 15 (chunks 0 and 1) up front; iteration k fetches the two rows of chunk k+2.
-            if (UPS == 1) {
-                for (int idx = tid; idx < (RING / 2) * (SW / 2); idx += NPT) {
-                    const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
-                    unsigned ab, cd;
-                    load_block(2 * sp2, t, y0, x0, ab, cd);
-                    store_block(2 * sp2, t, ab, cd);
-                }
-            } else {
-                for (int idx = tid; idx < RING * SW; idx += NPT) {
-                    const int s = idx / SW, sx = idx - s * SW;
-                    sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+            if (chain_warp) {
+                if (UPS == 1) {
+                    for (int idx = lt; idx < (RING / 2) * (SW / 2); idx += NBT) {
+                        const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
+                        unsigned ab, cd;
+                        load_block(2 * sp2, t, y0, x0, ab, cd);
+                        store_block(2 * sp2, t, ab, cd);
+                    }
+                } else {
+                    for (int idx = lt; idx < RING * SW; idx += NBT) {
+                        const int s = idx / SW, sx = idx - s * SW;
+                        sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                    }
                 }
             }
-            const int rl = tid / QW, q = tid - rl * QW;          // this thread's row of a chunk and chain column / pixel column
+            const int rl = lt / QW, q = lt - rl * QW;            // this thread's row of a chunk and chain column / pixel column
             // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
             // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
             auto stage_B = [&](int kb) {
@@ -250,24 +255,27 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             };
             const int nchunks = hh / RBP;
             group_sync(BAR_PROD, NPT);                                       // ring rows 0 .. 15 are in place
-            stage_B(0);
+            if (chain_warp) stage_B(0);
             for (int k = 0; k < nchunks; ++k) {
-                // fetch the ring rows of chunk k+2 (rows 2k+16, 2k+17: the slots of rows 2k, 2k+1, last read by B(k))
+                // chain warps: fetch the ring rows of chunk k+2 (rows 2k+16, 2k+17: the slots of rows 2k, 2k+1, last read by B(k))
                 const bool more = k + 2 < nchunks;
                 unsigned pab = 0u, pcd = 0u;
-                if (UPS == 1 && more && tid < SW / 2) load_block(RBP * k + RING, tid, y0, x0, pab, pcd);
+                if (UPS == 1 && chain_warp && more && lt < SW / 2) load_block(RBP * k + RING, lt, y0, x0, pab, pcd);
                 group_sync(BAR_PROD, NPT);                                   // B(k) complete in sQ[k & 1]; C(k-1) done with sQ[(k+1) & 1]; ring rows of chunk k+1 published
-                if (k + 1 < nchunks) stage_B(k + 1);
-                stage_C(k);
-                if (more) {
-                    if (UPS == 1) {
-                        if (tid < SW / 2) store_block(RBP * k + RING, tid, pab, pcd);
-                    } else {
-                        for (int idx = tid; idx < RBP * SW; idx += NPT) {
-                            const int s = RBP * k + RING + idx / SW, sx = idx % SW;
-                            sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                if (chain_warp) {
+                    if (k + 1 < nchunks) stage_B(k + 1);
+                    if (more) {
+                        if (UPS == 1) {
+                            if (lt < SW / 2) store_block(RBP * k + RING, lt, pab, pcd);
+                        } else {
+                            for (int idx = lt; idx < RBP * SW; idx += NBT) {
+                                const int s = RBP * k + RING + idx / SW, sx = idx % SW;
+                                sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                            }
                         }
                     }
+                } else {
+                    stage_C(k);
                 }
             }
             named_arrive(BAR_FULL + buf, NTP);                               // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
