@@ -8,6 +8,6 @@ for r in rows[hdr + 1:]:
     if len(r) > vi:
         agg[r[ki][:90]].append(float(r[vi].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
-print("command: ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv python bench.py --steps 2 --warmup 3")
+print("command: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     print("%-92s n=%4d avg=%10.1f %s share=%.3f" % (k, len(v), sum(v) / len(v), rows[hdr + 1][ui], sum(v) / tot))

@@ -1,31 +1,33 @@
-// raisr_pipe_kernel.cuh -- persistent, warp-specialised form of the RAISR pass kernel.
+// raisr_pipe_kernel.cuh -- persistent, warp-specialised form of the RAISR pass kernel (the default).
 //
 // Same arithmetic as raisr_pass_kernel (raisr_kernels.cuh: stages A-E, bit-identical results); what changes is the
 // schedule.  The profile of the phase-sequential kernel shows two kinds of stages: B/C (structure tensor + bucket) are
 // bound by FP32/ALU issue with the shared-memory pipe idle, D (121-tap filter out of the shared filter slice) is bound
-// by the shared-memory pipe with the FMA pipe idle.  Here one CTA per SM loops over tiles with two warp groups:
-//   producer warps : tile i+1 -- stream the upscaled rows through a 16-row ring, column chains, buckets  -> bucket tile[(i+1)&1]
-//   consumer warps : tile i   -- S tile, per-type filter slices (cp.async.bulk), 8-lane filter, blend, store
-// so the FMA-bound and the LSU-bound work of neighbouring tiles overlap on the same SM.  The hand-off is a pair of bucket
-// tiles guarded by hardware named barriers (bar.arrive / bar.sync, full and empty per tile buffer: the waiting side blocks
-// without consuming issue slots), group-local synchronisation uses two more named barriers.
+// by the shared-memory pipe with the FMA pipe idle.  Here one CTA per SM loops over tiles with three warp roles:
+//   chain warps  (8) : tile i+1 -- stream the upscaled rows through a 16-row ring, stage B column chains (FMUL2/FFMA2)
+//   bucket warps (8) : tile i+1 -- stage C: lane tree, eigen-analysis, hash              -> bucket tile[(i+1)&1]
+//   filter warps (12): tile i   -- S tile, per-type filter slices (cp.async.bulk), 8-lane filter, blend, store
+// so the FMA-bound, the latency-bound and the LSU-bound work overlap on the same SM.  The chain warps run one 2-row chunk
+// ahead of the bucket warps through a double-buffered chain buffer (one named barrier per chunk); producers and filter
+// warps hand over a pair of bucket tiles guarded by hardware named barriers (bar.arrive / bar.sync, full and empty per
+// tile buffer: the waiting side blocks without consuming issue slots).
 //
-// Register file: the CTA is launched with 80 registers per thread; the producer warpgroups drop to 48 and the consumer
-// warpgroups rise to 96 (setmaxnreg).  Producer: the upscaled rows of the next chunk are fetched from global memory before
-// stage B and stored into free ring slots after stage C (latency hidden); stage B uses packed FMUL2/FFMA2.
+// Register file: the CTA is launched with 72 registers per thread; the producer warpgroups drop to 48 and the filter
+// warpgroups rise to 104 (setmaxnreg).  The upscaled rows of chunk k+2 are fetched from global memory before the barrier
+// of chunk k and stored into free ring slots after stage B (latency hidden).
 //
-// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite), and the default: 8 producer + 16 consumer warps.
+// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite, tools/kbench.py); 0.63 ms vs 0.85 ms per 4K frame.
 #pragma once
 #include "raisr_kernels.cuh"
 
 namespace raisr {
 
-constexpr int NTP = 896;                     // threads per CTA of the pipelined kernel: 16 consumer + 8 chain + 8 bucket warps
+constexpr int NTP = 896;                     // threads per CTA of the pipelined kernel: 12 filter + 8 chain + 8 bucket warps
 constexpr int NPW = 16;                      // producer warps: 8 chain warps (stage B) + 8 bucket warps (stage C)
-constexpr int NCW = NTP / 32 - NPW;          // consumer warps (4 warpgroups)
+constexpr int NCW = NTP / 32 - NPW;          // filter (consumer) warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
 constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
-constexpr int PROD_REGS = 48, CONS_REGS = 104;    // setmaxnreg targets: 512*40 + 512*88 == 1024*64 registers of the CTA
+constexpr int PROD_REGS = 48, CONS_REGS = 104;   // setmaxnreg targets: 512*48 + 384*104 == 896*72 registers of the CTA
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
 static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
