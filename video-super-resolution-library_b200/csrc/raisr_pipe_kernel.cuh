@@ -382,46 +382,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int nrows = (hh - hfirst + JS - 1) / JS;
                 mbar_wait(mslice, nload & 1u);
                 ++nload;
-                auto block = [&](auto uu, const int h, const int jb) {
-                    constexpr int UU = decltype(uu)::value;
-                    const float *sp = sS + (h + 1) * SP + jb + 1;
-                    const unsigned char *hp = sHash + h * HP + jb;
-                    int hv[UU];
-#pragma unroll
-                    for (int u = 0; u < UU; ++u) hv[u] = (jb + 4 * JS * u < HW) ? hp[4 * JS * u] : 255;
-                    float a0[UU], a1[UU];
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        const float *q0 = sp + off[2 * n][0], *q1 = sp + off[2 * n][1], *q2 = sp + off[2 * n + 1][0], *q3 = sp + off[2 * n + 1][1];
-#pragma unroll
-                        for (int u = 0; u < UU; ++u) {
-                            const float4 f = sF4[(hv[u] == 255 ? 0 : hv[u]) * 32 + n * 8];
-                            const float p0 = q0[4 * JS * u], p1 = q1[4 * JS * u], p2 = q2[4 * JS * u], p3 = q3[4 * JS * u];
-                            if (n == 0) { a0[u] = fmul(p0, f.x); a1[u] = fmul(p1, f.y); }
-                            else { a0[u] = ffma(p0, f.x, a0[u]); a1[u] = ffma(p1, f.y, a1[u]); }
-                            a0[u] = ffma(p2, f.z, a0[u]);
-                            a1[u] = ffma(p3, f.w, a1[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UU; ++u) {
-                        const float cur = tree8(a0[u], a1[u], q);
-                        bool ok = (cur > flo) && (cur < fhi);                 // strict range test, Raisr.cpp:1192-1196
-                        float res = cur;
-                        const int j = jb + 4 * JS * u;
-                        if (has_ov) {
-                            const int c = x0 - 1 + j;
-                            const int hv2 = (j < HW && c >= p.tail_start && c < p.tail_start + OVW) ? sHash2[h * OVW + (c - p.tail_start)] : 255;
-                            const bool need2 = (hv2 != 255) && !ok && p.blending == 2;
-                            if (__any_sync(0xffffffffu, need2)) {
-                                const float cur16 = dot8(sp + 4 * JS * u, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
-                                if (need2 && cur16 > flo && cur16 < fhi) { ok = true; res = cur16; }
-                            }
-                        }
-                        if (q == 0 && hv[u] != 255 && ok) sHR[h * HP + j] = res;
-                    }
-                };
-                // Fast form of the block for tiles without 16/8-wide overlap columns: addresses = per-lane constant + uniform + immediate,
+                // One warp iteration = UU groups of 4 pixels of one tile row: addresses = per-lane constant + uniform + immediate,
                 // packed FMUL2/FFMA2 for the chain pair (2q, 2q+1), and the 16 -> 1 lane tree of the 4 pixel groups folded into 8 shuffles:
                 // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
                 // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
@@ -477,23 +438,46 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                         sts_f32(hroff + 4u * (unsigned)(h * HP + jc0), cur);
                 };
                 // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
-                // single pixel groups over all warps so that no warp waits a whole item at the barrier
+                // single pixel groups over all warps so that no warp waits a whole item at the barrier.  Items without a hashed
+                // pixel (rows outside [6, H-6), columns from c_end on) are skipped: HR stays S there.
                 const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
+                auto live = [&](int h, int jc0) {
+                    const int r = y0 - 1 + h;
+                    return r >= 6 && r < H - 6 && x0 - 1 + jc0 < p.c_end;
+                };
                 for (int it = cwarp; it < nfull; it += NCW) {
                     const int ri = it / NBLK, bi = it - ri * NBLK;
-                    const int h = hfirst + ri * JS;
-                    const int jb = jfirst + (bi * 4 * U + g) * JS;
-                    if (!has_ov) {
-                        if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jfirst + bi * 4 * U * JS);
-                        else fast_block(std::integral_constant<int, ULAST>{}, h, jfirst + bi * 4 * U * JS);
-                    } else if (bi < NBLK - 1) block(std::integral_constant<int, U>{}, h, jb);
-                    else block(std::integral_constant<int, ULAST>{}, h, jb);
+                    const int h = hfirst + ri * JS, jc0 = jfirst + bi * 4 * U * JS;
+                    if (!live(h, jc0)) continue;
+                    if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jc0);
+                    else fast_block(std::integral_constant<int, ULAST>{}, h, jc0);
                 }
                 for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
                     const int it = nfull + rq / U, u = rq - (rq / U) * U;
                     const int ri = it / NBLK, bi = it - ri * NBLK;
-                    if (bi == NBLK - 1 && u >= ULAST) continue;
-                    block(std::integral_constant<int, 1>{}, hfirst + ri * JS, jfirst + (bi * 4 * U + 4 * u + g) * JS);
+                    const int h = hfirst + ri * JS, jc0 = jfirst + (bi * 4 * U + 4 * u) * JS;
+                    if ((bi == NBLK - 1 && u >= ULAST) || !live(h, jc0)) continue;
+                    fast_block(std::integral_constant<int, 1>{}, h, jc0);
+                }
+                // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
+                // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
+                if (has_ov && p.blending == 2) {
+                    const int jlo = max(jfirst, p.tail_start - (x0 - 1)), jhi = min(HW, p.tail_start + OVW - (x0 - 1));
+                    const int j0 = jlo + ((jlo - jfirst) % JS != 0 ? JS - (jlo - jfirst) % JS : 0);   // first column of this type in the overlap
+                    const int ncol = (jhi > j0) ? (jhi - j0 + JS - 1) / JS : 0;
+                    const int total = nrows * ncol;
+                    for (int base = cwarp * 4; base < total; base += NCW * 4) {
+                        const int pi = min(base + g, total - 1);
+                        const int ri = pi / ncol, ci = pi - ri * ncol;
+                        const int h = hfirst + ri * JS, j = j0 + ci * JS;
+                        const int hv = sHash[h * HP + j];
+                        const int hv2 = sHash2[h * OVW + (x0 - 1 + j - p.tail_start)];
+                        const float *sp = sS + (h + 1) * SP + j + 1;
+                        const float cur8 = dot8(sp, sF + (hv == 255 ? 0 : hv) * 128, off, q);
+                        const float cur16 = dot8(sp, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
+                        const bool ok8 = cur8 > flo && cur8 < fhi;
+                        if (q == 0 && base + g < total && hv != 255 && hv2 != 255 && !ok8 && cur16 > flo && cur16 < fhi) sHR[h * HP + j] = cur16;
+                    }
                 }
                 group_sync(BAR_CONS, NCT);
             }
