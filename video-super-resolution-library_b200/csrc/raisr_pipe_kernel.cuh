@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
             r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
         };
-        const bool chain_warp = tid < NBT;                                   // sub-role: stage B (column chains) or stage C (buckets)
+        const bool chain_warp = tid >= NBT;                                  // sub-role: stage B (column chains) or stage C (buckets)
         const int lt = tid & (NBT - 1);
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
