@@ -52,7 +52,7 @@ __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("ba
 // producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
 // mbarrier spin), the signalling side does not wait (bar.arrive).  count = all threads of both sides.
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-constexpr int BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5;   // FULL/EMPTY + bucket tile index (0/1)
+constexpr int BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5, BAR_CHAIN = 7;   // FULL/EMPTY + bucket tile index (0/1)
 
 // Packed fp32 pairs (sm_100 FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, i.e. the same roundings as
 // two scalar instructions at half the issue slots.  Stage B keeps its chains for weight columns (m, m+1) in one 64-bit pair.
@@ -159,31 +159,17 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         };
         const bool chain_warp = tid >= NBT;                                  // sub-role: stage B (column chains) or stage C (buckets)
         const int lt = tid & (NBT - 1);
+        // The two producer roles run as one pipeline over all chunks of all tiles of this CTA: the chain warps are one chunk
+        // ahead of the bucket warps (double-buffered chains, buffer = running chunk number & 1, one BAR_PROD per chunk), also
+        // across tile boundaries, where the chain warps refill the ring while the bucket warps finish the previous tile.
         int iter = 0;
+        unsigned gk = 0;                                                     // running chunk number
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
             unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
             unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
-            if (iter >= 2) group_sync(BAR_EMPTY + buf, NTP);                 // the consumer is done with this bucket tile (tile i-2)
-            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1) reads
-            // rows 2k .. 2k+13.  Rows 0 .. 15 (chunks 0 and 1) up front; iteration k fetches the two rows of chunk k+2.
-            if (chain_warp) {
-                if (UPS == 1) {
-                    for (int idx = lt; idx < (RING / 2) * (SW / 2); idx += NBT) {
-                        const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
-                        unsigned ab, cd;
-                        load_block(2 * sp2, t, y0, x0, ab, cd);
-                        store_block(2 * sp2, t, ab, cd);
-                    }
-                } else {
-                    for (int idx = lt; idx < RING * SW; idx += NBT) {
-                        const int s = idx / SW, sx = idx - s * SW;
-                        sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
-                    }
-                }
-            }
             const int rl = lt / QW, q = lt - rl * QW;            // this thread's row of a chunk and chain column / pixel column
             // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
             // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
@@ -212,7 +198,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     }
                     vprev = vcur; vcur = vnext; row = nrow;
                 }
-                float *qd = sQ + (kb & 1) * QCHUNK + (rl * 18) * QW + q;
+                float *qd = sQ + ((gk + kb) & 1u) * QCHUNK + (rl * 18) * QW + q;
 #pragma unroll
                 for (int mm = 0; mm < 3; ++mm)
 #pragma unroll
@@ -230,7 +216,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int j = min(q, HW - 1);
                 const int r = y0 - 1 + h, c = x0 - 1 + j;
                 float g[3];
-                const float *qs = sQ + (kc & 1) * QCHUNK + (rl * 18) * QW + j;
+                const float *qs = sQ + ((gk + kc) & 1u) * QCHUNK + (rl * 18) * QW + j;
 #pragma unroll
                 for (int k3 = 0; k3 < 3; ++k3) {
                     float lane[11];
@@ -256,31 +242,50 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 }
             };
             const int nchunks = hh / RBP;
-            group_sync(BAR_PROD, NPT);                                       // ring rows 0 .. 15 are in place
-            if (chain_warp) stage_B(0);
-            for (int k = 0; k < nchunks; ++k) {
-                // chain warps: fetch the ring rows of chunk k+2 (rows 2k+16, 2k+17: the slots of rows 2k, 2k+1, last read by B(k))
-                const bool more = k + 2 < nchunks;
-                unsigned pab = 0u, pcd = 0u;
-                if (UPS == 1 && chain_warp && more && lt < SW / 2) load_block(RBP * k + RING, lt, y0, x0, pab, pcd);
-                group_sync(BAR_PROD, NPT);                                   // B(k) complete in sQ[k & 1]; C(k-1) done with sQ[(k+1) & 1]; ring rows of chunk k+1 published
-                if (chain_warp) {
-                    if (k + 1 < nchunks) stage_B(k + 1);
+            if (chain_warp) {
+                // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1)
+                // reads rows 2k .. 2k+13.  Rows 0 .. 13 up front (the previous tile's last B is done: BAR_PROD), every chunk then
+                // fetches the two rows of the NEXT chunk into the slots of rows 2k-2, 2k-1.
+                if (UPS == 1) {
+                    for (int idx = lt; idx < ((RING - RBP) / 2) * (SW / 2); idx += NBT) {
+                        const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
+                        unsigned ab, cd;
+                        load_block(2 * sp2, t, y0, x0, ab, cd);
+                        store_block(2 * sp2, t, ab, cd);
+                    }
+                } else {
+                    for (int idx = lt; idx < (RING - RBP) * SW; idx += NBT) {
+                        const int s = idx / SW, sx = idx - s * SW;
+                        sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                    }
+                }
+                group_sync(BAR_CHAIN, NBT);
+                for (int k = 0; k < nchunks; ++k) {
+                    const bool more = k + 1 < nchunks;
+                    unsigned pab = 0u, pcd = 0u;
+                    if (UPS == 1 && more && lt < SW / 2) load_block(RBP * k + RING - RBP, lt, y0, x0, pab, pcd);
+                    stage_B(k);
                     if (more) {
                         if (UPS == 1) {
-                            if (lt < SW / 2) store_block(RBP * k + RING, lt, pab, pcd);
+                            if (lt < SW / 2) store_block(RBP * k + RING - RBP, lt, pab, pcd);
                         } else {
                             for (int idx = lt; idx < RBP * SW; idx += NBT) {
-                                const int s = RBP * k + RING + idx / SW, sx = idx % SW;
+                                const int s = RBP * k + RING - RBP + idx / SW, sx = idx % SW;
                                 sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
                             }
                         }
                     }
-                } else {
+                    group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
+                }
+            } else {
+                if (iter >= 2) group_sync(BAR_EMPTY + buf, NBT + NCT);       // the filter warps are done with this bucket tile (tile i-2)
+                for (int k = 0; k < nchunks; ++k) {
+                    group_sync(BAR_PROD, NPT);                               // B(k) is complete
                     stage_C(k);
                 }
+                named_arrive(BAR_FULL + buf, NBT + NCT);                     // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
             }
-            named_arrive(BAR_FULL + buf, NTP);                               // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
+            gk += (unsigned)nchunks;
         }
     } else {
         // =========================== consumer: filter + blend of tile i ===========================
@@ -361,7 +366,8 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int h = idx / HW, j = idx - h * HW;
                 sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
             }
-            group_sync(BAR_FULL + buf, NTP);                                  // buckets of this tile are ready (also publishes S / HR to the group)
+            group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
+            group_sync(BAR_FULL + buf, NBT + NCT);                            // buckets of this tile are ready
 
             // ---- D: 121-tap filter, one pixel type at a time ----
             const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             // ---- E: blend + store ----
             stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
             group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
-            if (tile + 2 * (int)gridDim.x < ntiles) named_arrive(BAR_EMPTY + buf, NTP);   // bucket tile may be refilled (tile i+2)
+            if (tile + 2 * (int)gridDim.x < ntiles) named_arrive(BAR_EMPTY + buf, NBT + NCT);   // bucket tile may be refilled (tile i+2)
             if (p.band_done && ct == 0) {
                 __threadfence();
                 atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
