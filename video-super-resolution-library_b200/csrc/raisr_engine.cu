@@ -123,7 +123,7 @@ struct raisr_cuda_engine {
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
     int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
-    int zero_copy = 2;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (measured +4 % end to end); RAISR_CUDA_ZERO_COPY overrides
+    int zero_copy = 0;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
     int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
     bool use_pipe = true;           // persistent warp-specialised kernel (0.74 ms per 4K frame); RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (0.85 ms)
     float *d_filters[2] = {nullptr, nullptr};
@@ -141,15 +141,21 @@ struct raisr_cuda_engine {
     cudaEvent_t ev_uv = nullptr, ev_in = nullptr;
     unsigned long long launches = 0;
     // host-pointer pipeline: the final pass signals finished row bands, the D2H stream waits on the counters
-    static constexpr int kMaxBands = 8;
+    static constexpr int kMaxBands = 16;
     unsigned *d_band_done = nullptr;
     cudaStream_t stream_d2h = nullptr;
     typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
     WaitValue32Fn wait_value32 = nullptr, write_value32 = nullptr;
     unsigned *d_in_ready = nullptr;      // per input band: sequence number of the last frame whose rows have arrived
     unsigned frame_seq = 0;
+    // RAISR_CUDA_TIMING=1: per-stage device times of the host-pointer call, printed when the engine is destroyed
+    bool timing = false; cudaEvent_t tev[3] = {nullptr, nullptr, nullptr}; double t_h2d = 0, t_kern = 0; unsigned long long t_n = 0;
+    unsigned *d_chroma_ready = nullptr;  // [0] sequence number of the last frame whose chroma planes have arrived (H2D on stream_uv), [1] CTAs done with them (running total)
+    unsigned chroma_seq = 0, chroma_done_target = 0;
+    unsigned band_target[kMaxBands] = {};  // running totals the D2H stream waits for, per output row band
     cudaStream_t stream_h2d = nullptr;
     int last_grid_y = 0, last_tile_h = 0;   // geometry of the most recent pass launch
+    int last_grid_x = 0;                    // CTAs of the most recent launch that carried a chroma job
 };
 
 namespace {
@@ -188,6 +194,7 @@ int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStre
     if (e->use_pipe) {
         // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
         const int ntiles = (int)(grid.x * grid.y);
+        if (q.chroma_n) e->last_grid_x = std::min(ntiles, e->num_sms);
         raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NTP, PIPE_SMEM_BYTES, s>>>(q);
     } else if (e->cluster == 2 && (grid.x % 2 == 0)) {
         // pairs of horizontally neighbouring tiles form a thread-block cluster and share every filter-slice load
@@ -287,14 +294,38 @@ void set_upscale(const raisr_cuda_engine *e, PassParams *p)
     p->up_src_h = e->up_src_h;
 }
 
+// chroma planes handed to the pipelined kernel (resized by its producer warps, no launch of their own)
+struct ChromaJob {
+    const void *in[2]; size_t in_step[2];
+    void *out[2]; size_t out_step[2];
+    const unsigned *ready; unsigned seq;       // optional H2D completion flag
+    unsigned *done;                            // optional per-CTA completion counter
+};
+
+void set_chroma(const raisr_cuda_engine *e, const ChromaJob *c, PassParams *p)
+{
+    if (!c) return;
+    p->chroma_n = 2;
+    for (int i = 0; i < 2; ++i) {
+        p->chroma[i].in = c->in[i]; p->chroma[i].in_pitch = c->in_step[i];
+        p->chroma[i].out = c->out[i]; p->chroma[i].out_pitch = c->out_step[i];
+    }
+    p->c_in_w = e->in_cw; p->c_in_h = e->in_ch; p->c_W = e->out_cw; p->c_H = e->out_ch;
+    p->c_xmap = e->cx.d_map; p->c_xw = e->cx.d_w; p->c_ymap = e->cy.d_map; p->c_yw = e->cy.d_w;
+    p->c_denx = e->cx.den; p->c_deny = e->cy.den;
+    p->chroma_ready = c->ready; p->chroma_seq = c->seq; p->chroma_done = c->done;
+}
+
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
-             cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0)
+             cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0,
+             const ChromaJob *chroma = nullptr)
 {
     const bool two = e->cfg.passes == 2;
     const bool mode2 = two && e->cfg.two_pass_mode == 2;
     if (!two) {
         PassParams p{};
+        set_chroma(e, chroma, &p);
         p.in = in_y; p.in_pitch = in_step; p.in_w = e->in_w; p.in_h = e->in_h;
         p.out = out_y; p.out_pitch = out_step; p.W = e->out_w; p.H = e->out_h; p.row0 = row0; p.row1 = row1;
         pass_common(e, 0, p.W, &p);
@@ -327,6 +358,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     if (mode2) set_upscale(e, &p2);
     p2.band_done = band_done;
     p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows;
+    set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
     int rc = launch_pass(e, p1, s);
     if (rc) return rc;
     return launch_pass(e, p2, s);
@@ -414,6 +446,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
     if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
+    if (std::getenv("RAISR_CUDA_TIMING")) { e->timing = true; for (auto &ev : e->tev) cudaEventCreate(&ev); }
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
         // contiguous bytes per step: tap k = 16m + j  ->  position (m/2)*32 + (j/2)*4 + (m%2)*2 + (j%2)   (see dot8())
@@ -456,7 +489,8 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
                 return fail(RNLErrorInsufficientResources);
     }
     if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
-    if (cudaMalloc(&e->d_in_ready, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+    if (cudaMalloc(&e->d_chroma_ready, 2 * sizeof(unsigned)) != cudaSuccess || cudaMemset(e->d_chroma_ready, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&e->d_in_ready, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
         cudaMemset(e->d_in_ready, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&e->d_band_done, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
@@ -545,9 +579,19 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
                               void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending, void *stream)
 {
     if (!e || !e->have_res) return RNLErrorBadParameter;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->use_pipe && in_u && out_u && in_v && out_v && in_y && out_y) {
+        // one launch per pass: the chroma planes ride along with the (first) luma launch
+        if (check_blending(blending)) return RNLErrorBadParameter;
+        e->blending = blending;
+        CUDA_OK(cudaSetDevice(e->device));
+        for (unsigned i = 0; i < e->cfg.passes; ++i)
+            if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
+        const ChromaJob cj{{in_u, in_v}, {in_u_step, in_v_step}, {out_u, out_v}, {out_u_step, out_v_step}, nullptr, 0, nullptr};
+        return run_luma(e, in_y, in_y_step, out_y, out_y_step, 0, e->out_h, s, nullptr, nullptr, 0, &cj);
+    }
     int rc = raisr_cuda_process_device_rows(e, in_y, in_y_step, out_y, out_y_step, blending, 0, e->out_h, stream);
     if (rc) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (in_u && out_u) { rc = launch_resize(e, in_u, in_u_step, out_u, out_u_step, s); if (rc) return rc; }
     if (in_v && out_v) { rc = launch_resize(e, in_v, in_v_step, out_v, out_v_step, s); if (rc) return rc; }
     return RNLErrorNone;
@@ -563,89 +607,137 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     CUDA_OK(cudaSetDevice(e->device));
     const size_t bps = e->bps;
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
-    // chroma on its own stream: copies and the two resizes overlap the luma kernel
-    if (chroma) {
+    const bool memops = e->wait_value32 && e->write_value32;       // stream memory operations (cuStreamWaitValue32 / WriteValue32)
+    auto memop_failed = [](const char *what) { std::cout << "[RAISR ERROR] " << what << " failed" << std::endl; return (int)RNLErrorUndefined; };
+    // Pipelined kernel: the chroma planes are resized by the luma launch itself (its filter warps, early in the frame, while
+    // they would otherwise wait for the first bucket tiles); only the copies remain here.  Phase-sequential kernel: chroma on
+    // its own stream, both H2D copies and both resizes first, the D2H copies overlap the luma kernel.
+    const bool fused = chroma && e->use_pipe;
+    if (chroma && !fused) {
         const void *src[2] = {in_u, in_v};
         const size_t sstep[2] = {in_u_step, in_v_step};
-        void *dst[2] = {out_u, out_v};
-        const size_t dstep[2] = {out_u_step, out_v_step};
         for (int i = 0; i < 2; ++i) {
             CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
                                       cudaMemcpyHostToDevice, e->stream_uv));
             int rc = launch_resize(e, e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->stream_uv);
             if (rc) return rc;
+        }
+        void *dst[2] = {out_u, out_v};
+        const size_t dstep[2] = {out_u_step, out_v_step};
+        for (int i = 0; i < 2; ++i)
             CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
                                       cudaMemcpyDeviceToHost, e->stream_uv));
-        }
     }
-    // Pinned (page-locked, device-mapped) caller planes can be used in place: the pass kernel reads the input tile
-    // rows / writes the finished 4-pixel groups straight over PCIe, spread over the whole kernel, instead of a serial
-    // H2D before and D2H copies after it.  Pageable planes (FFmpeg's default allocator) go through the copy pipeline.
+
+    // ---- luma input -------------------------------------------------------------------------------------------------------
+    // in place (pinned planes, RAISR_CUDA_ZERO_COPY bit 0; measured slower), in row bands on the H2D stream with the kernel
+    // launched first and waiting per tile for the rows it reads (RAISR_CUDA_H2D_BANDS), or one copy ahead of the kernel.
     const void *k_in = e->d_in[0].ptr;
     size_t k_in_step = e->d_in[0].pitch;
-    void *k_out = e->d_out[0].ptr;
-    size_t k_out_step = e->d_out[0].pitch;
     const bool in_direct = (e->zero_copy & 1) && mapped_host_pointer(in_y, &k_in);
     if (in_direct) k_in_step = in_y_step;
     const unsigned *in_ready = nullptr;
     int in_band_rows = 0;
-    bool banded_h2d = false;
-    if (!in_direct) {
-        const int nb = e->h2d_bands;
-        if (nb > 1 && e->write_value32 && !e->use_pipe) {
-            // banded H2D on its own stream; after each band the stream writes this frame's sequence number into the band's
-            // flag.  The pass kernel is launched FIRST and each tile waits only for the input rows it reads.
-            ++e->frame_seq;
-            in_band_rows = (e->in_h + nb - 1) / nb;
-            in_ready = e->d_in_ready;
-            banded_h2d = true;
+    const bool banded_h2d = !in_direct && e->h2d_bands > 1 && memops && !e->use_pipe;   // (the pipelined kernel: measured no gain, costs registers)
+    if (banded_h2d) {
+        ++e->frame_seq;
+        in_band_rows = (e->in_h + e->h2d_bands - 1) / e->h2d_bands;
+        in_ready = e->d_in_ready;
+    } else if (!in_direct) {
+        if (e->timing) cudaEventRecord(e->tev[0], e->stream);
+        CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+        if (e->timing) cudaEventRecord(e->tev[1], e->stream);
+        if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream));   // the chroma copies queue up behind the luma copy (same copy engine)
+    }
+
+    // ---- chroma job of the pipelined kernel -----------------------------------------------------------------------------
+    ChromaJob cj{};
+    bool chroma_early_d2h = false;
+    if (fused) {
+        for (int i = 0; i < 2; ++i) {
+            cj.in[i] = e->d_in[i + 1].ptr; cj.in_step[i] = e->d_in[i + 1].pitch;
+            cj.out[i] = e->d_out[i + 1].ptr; cj.out_step[i] = e->d_out[i + 1].pitch;
+        }
+        if (memops) {
+            cj.ready = e->d_chroma_ready; cj.seq = ++e->chroma_seq;          // H2D on the chroma stream, flagged to the running kernel
+            cj.done = e->d_chroma_ready + 1; chroma_early_d2h = true;        // D2H by the copy engine as soon as every CTA has written its share
         } else {
-            CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+            const void *src[2] = {in_u, in_v};
+            const size_t sstep[2] = {in_u_step, in_v_step};
+            for (int i = 0; i < 2; ++i)
+                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                          cudaMemcpyHostToDevice, e->stream));
         }
     }
-    auto enqueue_h2d_bands = [&]() -> int {
-        if (!banded_h2d) return 0;
-        for (int b = 0; b * in_band_rows < e->in_h; ++b) {
-            const int r0 = b * in_band_rows, rows = std::min(in_band_rows, e->in_h - r0);
-            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)r0 * e->d_in[0].pitch, e->d_in[0].pitch,
-                                      static_cast<const char *>(in_y) + (size_t)r0 * in_y_step, in_y_step, e->in_w * bps, rows,
-                                      cudaMemcpyHostToDevice, e->stream_h2d));
-            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)(e->d_in_ready + b), e->frame_seq, 0) != 0) {
-                std::cout << "[RAISR ERROR] cuStreamWriteValue32 failed" << std::endl;
-                return RNLErrorUndefined;
+    // after the launch: banded luma H2D, chroma H2D behind it, chroma D2H once the kernel says the planes are written
+    auto after_launch = [&]() -> int {
+        if (banded_h2d) {
+            for (int b = 0; b * in_band_rows < e->in_h; ++b) {
+                const int r0 = b * in_band_rows, rows = std::min(in_band_rows, e->in_h - r0);
+                CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)r0 * e->d_in[0].pitch, e->d_in[0].pitch,
+                                          static_cast<const char *>(in_y) + (size_t)r0 * in_y_step, in_y_step, e->in_w * bps, rows,
+                                          cudaMemcpyHostToDevice, e->stream_h2d));
+                if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)(e->d_in_ready + b), e->frame_seq, 0) != 0)
+                    return memop_failed("cuStreamWriteValue32");
             }
+            if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));
         }
+        if (!fused) return 0;
+        void *dst[2] = {out_u, out_v};
+        const size_t dstep[2] = {out_u_step, out_v_step};
+        if (!memops) {                                                       // planes were copied in ahead of the kernel; out after it
+            for (int i = 0; i < 2; ++i)
+                CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
+                                          cudaMemcpyDeviceToHost, e->stream));
+            return 0;
+        }
+        const void *src[2] = {in_u, in_v};
+        const size_t sstep[2] = {in_u_step, in_v_step};
+        if (!in_direct) CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
+        for (int i = 0; i < 2; ++i)
+            CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                      cudaMemcpyHostToDevice, e->stream_uv));
+        if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+        e->chroma_done_target += (unsigned)e->last_grid_x;                   // running total: no reset, no race with the previous frame
+        if (e->wait_value32(e->stream_uv, (unsigned long long)(uintptr_t)(e->d_chroma_ready + 1), e->chroma_done_target, 0 /* GEQ */) != 0)
+            return memop_failed("cuStreamWaitValue32");
+        for (int i = 0; i < 2; ++i)
+            CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
+                                      cudaMemcpyDeviceToHost, e->stream_uv));
         return 0;
     };
-    const void *out_dev = nullptr;
-    const bool out_direct = (e->zero_copy & 2) && mapped_host_pointer(out_y, &out_dev);
-    if (out_direct) { k_out = const_cast<void *>(out_dev); k_out_step = out_y_step; }
+    (void)chroma_early_d2h;
+    const ChromaJob *cjp = fused ? &cj : nullptr;
+
     for (unsigned i = 0; i < e->cfg.passes; ++i)
         if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
-    const bool pipelined = !out_direct && e->wait_value32 != nullptr && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
+
+    // ---- luma output ------------------------------------------------------------------------------------------------------
+    const void *out_dev = nullptr;
+    const bool out_direct = (e->zero_copy & 2) && mapped_host_pointer(out_y, &out_dev);
+    const bool band_d2h = !out_direct && memops && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
     if (out_direct) {
-        int rc = run_luma(e, k_in, k_in_step, k_out, k_out_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows);
+        // pinned caller plane written in place by the final pass (small PCIe writes from the SMs, spread over the kernel)
+        int rc = run_luma(e, k_in, k_in_step, const_cast<void *>(out_dev), out_y_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp);
         if (rc) return rc;
-        if ((rc = enqueue_h2d_bands())) return rc;
+        if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+        if ((rc = after_launch())) return rc;
         CUDA_OK(cudaStreamSynchronize(e->stream));
-    } else if (pipelined) {
-        // The final pass counts finished tiles per row band; the D2H stream waits on each counter and copies that band
-        // while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
-        CUDA_OK(cudaMemsetAsync(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands, e->stream));
-        CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows);
+    } else if (band_d2h) {
+        // The final pass counts finished tiles per row band (running totals, never reset); the D2H stream waits on each counter
+        // and copies that band while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows, cjp);
         if (rc) return rc;
-        if ((rc = enqueue_h2d_bands())) return rc;
-        CUDA_OK(cudaStreamWaitEvent(e->stream_d2h, e->ev_in, 0));      // counters are zeroed before anybody waits on them
+        if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+        if ((rc = after_launch())) return rc;
         const int gx = (e->out_w + TW - 1) / TW;
         const int bty = (e->last_grid_y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
         for (int b = 0, ty = 0; ty < e->last_grid_y; ++b, ty += bty) {
             const int tiles_y = std::min(bty, e->last_grid_y - ty);
             const int r0 = ty * e->last_tile_h, r1 = std::min(e->out_h, (ty + tiles_y) * e->last_tile_h);
-            if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), (unsigned)(tiles_y * gx), 0 /* GEQ */) != 0) {
-                std::cout << "[RAISR ERROR] cuStreamWaitValue32 failed" << std::endl;
-                return RNLErrorUndefined;
-            }
+            e->band_target[b] += (unsigned)(tiles_y * gx);
+            if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), e->band_target[b], 0 /* GEQ */) != 0)
+                return memop_failed("cuStreamWaitValue32");
             CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(out_y) + (size_t)r0 * out_y_step, out_y_step,
                                       static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
                                       e->out_w * bps, r1 - r0, cudaMemcpyDeviceToHost, e->stream_d2h));
@@ -653,13 +745,19 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
         CUDA_OK(cudaStreamSynchronize(e->stream));
     } else {
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp);
         if (rc) return rc;
-        if ((rc = enqueue_h2d_bands())) return rc;
         CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
+        if ((rc = after_launch())) return rc;
         CUDA_OK(cudaStreamSynchronize(e->stream));
     }
+    if (banded_h2d) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
     if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
+    if (e->timing && !in_direct && !banded_h2d) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e->tev[0], e->tev[1]); cudaEventElapsedTime(&b, e->tev[1], e->tev[2]);
+        e->t_h2d += a; e->t_kern += b; e->t_n++;
+    }
     return RNLErrorNone;
 }
 
@@ -682,6 +780,7 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    if (e->timing && e->t_n) std::cout << "[RAISR TIMING] frames " << e->t_n << " luma H2D " << 1e3 * e->t_h2d / e->t_n << " us, memset+kernel " << 1e3 * e->t_kern / e->t_n << " us" << std::endl;
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_hash[i]); }
     for (int i = 0; i < 4; ++i) cudaFree(e->d_lut[i]);
     for (int i = 0; i < 3; ++i) { e->d_in[i].release(); e->d_out[i].release(); }
@@ -691,6 +790,7 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     if (e->stream_d2h) cudaStreamDestroy(e->stream_d2h);
     if (e->stream_h2d) cudaStreamDestroy(e->stream_h2d);
     cudaFree(e->d_in_ready);
+    cudaFree(e->d_chroma_ready);
     cudaFree(e->d_band_done);
     if (e->stream_uv) cudaStreamDestroy(e->stream_uv);
     if (e->ev_uv) cudaEventDestroy(e->ev_uv);

@@ -60,6 +60,16 @@ struct PassParams {
     float quarter, half;     // X86 8-wide hash constants
     int *hash_out;           // optional [H][W] bucket plane (parity tests), -1 = not hashed
     int blending;            // 2 = CountOfBitsChanged
+    // optional chroma planes resized by the pipelined kernel's producer warps once they have run out of luma tiles (the
+    // filter warps are still busy with the last tile then): Raisr.cpp:1373-1388 without a launch of its own
+    int chroma_n;            // 0, or the number of planes in chroma[]
+    struct { const void *in; size_t in_pitch; void *out; size_t out_pitch; } chroma[2];
+    int c_in_w, c_in_h, c_W, c_H;
+    const int *c_xmap, *c_xw, *c_ymap, *c_yw;
+    int c_denx, c_deny;
+    const unsigned *chroma_ready;   // optional: set to chroma_seq once the planes' H2D copies have landed
+    unsigned chroma_seq;
+    unsigned *chroma_done;          // optional: incremented once per CTA when its share of the chroma planes is written
     const uint2 *lut_rsqrt14, *lut_rcp14;      // x86 numerics: (c0,c1) runs of the 14-bit instructions, 128 entries each (may be null)
     const uint16_t *lut_rsqrtps, *lut_rcpps;   // x86 numerics: SSE approximation tables, 2048 entries each (may be null)
 };

@@ -94,6 +94,104 @@ __device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
     return load_S<PixT>(p, Yc, Xc, UPS != 0);
 }
 
+// Chroma planes: plain cheap upscale (Raisr.cpp:1373-1388) of this CTA's share of the planes, slice sl of nslices, by the filter
+// warps (NCT threads, ct = thread index in the group).  Not inlined: keeps its registers out of the filter loop's allocation.
+template <typename PixT>
+__device__ __noinline__ void chroma_slice_fn(const PassParams &p, int sl, int nslices, int ct)
+{
+    if (sl == 0 && p.chroma_ready) {                                 // the planes' H2D copies run on their own stream
+        if (ct == 0) {
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.chroma_ready) : "memory");
+            } while (v != p.chroma_seq);
+        }
+        group_sync(BAR_CONS, NCT);
+    }
+    if (p.c_W == 2 * p.c_in_w && p.c_H == 2 * p.c_in_h && p.c_denx == 4 && p.c_deny == 4) {
+        // exact 2x: one item = 2 output rows x 8 output columns from a 3 x 6 low-res window (replicate border = clamped
+        // coordinates); even outputs weigh low-res (i-1, i) by (1,3), odd outputs (i, i+1) by (3,1): (9a+3b+3c+d+8)>>4
+        const int gw8 = (p.c_W + 7) / 8, per_plane8 = gw8 * p.c_in_h;
+        const long long total8 = (long long)p.chroma_n * per_plane8;
+        const int c0 = (int)(total8 * blockIdx.x / gridDim.x), c1 = (int)(total8 * (blockIdx.x + 1) / gridDim.x);
+        const int s0 = c0 + (int)((long long)(c1 - c0) * sl / nslices), s1 = c0 + (int)((long long)(c1 - c0) * (sl + 1) / nslices);
+        for (int idx = s0 + ct; idx < s1; idx += NCT) {
+            const int pl = idx / per_plane8, rem = idx - pl * per_plane8;
+            const int jb = rem / gw8, ib = rem - jb * gw8;
+            const char *ibase = static_cast<const char *>(p.chroma[pl].in);
+            const PixT *rows[3] = {reinterpret_cast<const PixT *>(ibase + (size_t)max(jb - 1, 0) * p.chroma[pl].in_pitch),
+                                   reinterpret_cast<const PixT *>(ibase + (size_t)jb * p.chroma[pl].in_pitch),
+                                   reinterpret_cast<const PixT *>(ibase + (size_t)min(jb + 1, p.c_in_h - 1) * p.chroma[pl].in_pitch)};
+            unsigned L[3][6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) L[r][k] = rows[r][min(max(4 * ib - 1 + k, 0), p.c_in_w - 1)];
+            unsigned o[2][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int m = e >> 1;
+                unsigned h[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) h[r] = (e & 1) ? 3u * L[r][m + 1] + L[r][m + 2] : L[r][m] + 3u * L[r][m + 1];
+                o[0][e] = (h[0] + 3u * h[1] + 8u) >> 4;
+                o[1][e] = (3u * h[1] + h[2] + 8u) >> 4;
+            }
+            const int X = 8 * ib;
+#pragma unroll
+            for (int yy = 0; yy < 2; ++yy) {
+                PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.chroma[pl].out) + (size_t)(2 * jb + yy) * p.chroma[pl].out_pitch) + X;
+                const bool vec = (reinterpret_cast<uintptr_t>(orow) % (8 * sizeof(PixT))) == 0 && X + 7 < p.c_W;
+                if (vec && sizeof(PixT) == 1) {
+                    *reinterpret_cast<uint2 *>(orow) = make_uint2(o[yy][0] | (o[yy][1] << 8) | (o[yy][2] << 16) | (o[yy][3] << 24),
+                                                                 o[yy][4] | (o[yy][5] << 8) | (o[yy][6] << 16) | (o[yy][7] << 24));
+                } else if (vec) {
+                    *reinterpret_cast<uint4 *>(orow) = make_uint4(o[yy][0] | (o[yy][1] << 16), o[yy][2] | (o[yy][3] << 16),
+                                                                 o[yy][4] | (o[yy][5] << 16), o[yy][6] | (o[yy][7] << 16));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (X + e < p.c_W) orow[e] = (PixT)o[yy][e];
+                }
+            }
+        }
+    } else {
+    PassParams pc{};
+    pc.in_w = p.c_in_w; pc.in_h = p.c_in_h; pc.xmap = p.c_xmap; pc.xw = p.c_xw; pc.ymap = p.c_ymap; pc.yw = p.c_yw;
+    pc.denx = p.c_denx; pc.deny = p.c_deny;
+    const int gw = (p.c_W + 3) / 4;
+    const int per_plane = gw * p.c_H;
+    const long long total = (long long)p.chroma_n * per_plane;
+    const int c0 = (int)(total * blockIdx.x / gridDim.x), c1 = (int)(total * (blockIdx.x + 1) / gridDim.x);   // this CTA's groups
+    const int s0 = c0 + (int)((long long)(c1 - c0) * sl / nslices), s1 = c0 + (int)((long long)(c1 - c0) * (sl + 1) / nslices);
+    for (int idx = s0 + ct; idx < s1; idx += NCT) {
+        const int pl = idx / per_plane, rem = idx - pl * per_plane;
+        const int Y = rem / gw, X = (rem - Y * gw) * 4;
+        pc.in = p.chroma[pl].in; pc.in_pitch = p.chroma[pl].in_pitch;
+        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.chroma[pl].out) + (size_t)Y * p.chroma[pl].out_pitch) + X;
+        unsigned v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (X + e < p.c_W) ? (unsigned)(int)load_S<PixT>(pc, Y, X + e, true) : 0u;
+        const bool vec = ((reinterpret_cast<uintptr_t>(orow) % (4 * sizeof(PixT))) == 0) && X + 3 < p.c_W;
+        if (vec) {
+            if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            else *reinterpret_cast<uint2 *>(orow) = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (X + e < p.c_W) orow[e] = (PixT)v[e];
+        }
+    }
+    }
+    if (sl == nslices - 1 && p.chroma_done) {                        // this CTA's share is written: tell the host's copy stream
+        group_sync(BAR_CONS, NCT);
+        if (ct == 0) {
+            __threadfence();
+            atomicAdd(p.chroma_done, 1u);
+        }
+    }
+}
+
 template <typename PixT, int PT, int UPS>
 __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParams p)
 {
@@ -319,6 +417,13 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             }
         const unsigned fbase = smem_u32(sF) + 16u * (unsigned)q;          // this lane's 16 bytes of every 128-byte filter step
         const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
+        // ---- chroma planes: plain cheap upscale (Raisr.cpp:1373-1388), 4 pixels per thread.  This CTA's share of the planes is
+        // cut into up to three slices, one per tile from the second tile on, done while the filter warps would otherwise wait for
+        // the bucket tile: no launch of its own, and finished early enough for the host to copy the planes out under the kernel.
+        const int cta_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int nslices = min(3, max(1, cta_tiles - 1));                   // early in the frame: the host may copy the planes out while the luma runs on
+        int slices_done = 0;
+        auto chroma_slice = [&](int sl) { chroma_slice_fn<PixT>(p, sl, nslices, ct); };
         unsigned nload = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
@@ -366,6 +471,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int h = idx / HW, j = idx - h * HW;
                 sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
             }
+            if (p.chroma_n > 0 && iter >= 1 && slices_done < nslices) chroma_slice(slices_done++);
             group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
             group_sync(BAR_FULL + buf, NBT + NCT);                            // buckets of this tile are ready
 
@@ -496,6 +602,8 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
             }
         }
+        if (p.chroma_n > 0)
+            while (slices_done < nslices) chroma_slice(slices_done++);       // CTAs with fewer than three tiles
     }
 }
 
