@@ -123,7 +123,7 @@ struct raisr_cuda_engine {
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
     int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
-    int zero_copy = 0;              // bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
+    int zero_copy = 4;              // bit 2: write the rows of the last round of tiles straight into a pinned output plane (no copy after the kernel), bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
     int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
     bool use_pipe = true;           // persistent warp-specialised kernel (0.74 ms per 4K frame); RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (0.85 ms)
     float *d_filters[2] = {nullptr, nullptr};
@@ -156,6 +156,7 @@ struct raisr_cuda_engine {
     cudaStream_t stream_h2d = nullptr;
     int last_grid_y = 0, last_tile_h = 0;   // geometry of the most recent pass launch
     int last_grid_x = 0;                    // CTAs of the most recent launch that carried a chroma job
+    int last_banded_rows = 0;               // tile rows of the most recent launch that are signalled per band (the rest is written in place)
 };
 
 namespace {
@@ -226,8 +227,18 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
     q.tile_h = std::min(thmax, (((rows + ny - 1) / ny) + 1) & ~1);
     const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
     e->last_grid_y = (int)grid.y; e->last_tile_h = q.tile_h;
-    if (q.band_done) q.band_tiles_y = ((int)grid.y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
-    q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch) % (4 * sizeof(PixT))) == 0;
+    // tile rows of the last round of the persistent kernel (they finish together, at the very end): written in place into the
+    // caller's pinned plane when there is one, so that no copy remains after the kernel; the bands cover the rows above
+    int banded_rows = (int)grid.y;
+    if (q.out_tail && e->use_pipe) {
+        banded_rows = std::max(0, (int)grid.y - ((e->num_sms + gx - 1) / gx + 1));
+        q.tail_row0 = p.row0 + banded_rows * q.tile_h;
+    } else {
+        q.out_tail = nullptr;
+    }
+    e->last_banded_rows = banded_rows;
+    if (q.band_done) q.band_tiles_y = std::max(1, (banded_rows + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands);
+    q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch | reinterpret_cast<uintptr_t>(q.out_tail) | (q.out_tail ? q.out_tail_pitch : 0)) % (4 * sizeof(PixT))) == 0;
     // 2x fast path: exact factor 2 in both axes and even band origin
     const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
     const int ups = !p.upscale ? 0 : (fast2x ? 1 : 2);
@@ -319,7 +330,7 @@ void set_chroma(const raisr_cuda_engine *e, const ChromaJob *c, PassParams *p)
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
              cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0,
-             const ChromaJob *chroma = nullptr)
+             const ChromaJob *chroma = nullptr, void *out_tail = nullptr, size_t out_tail_step = 0)
 {
     const bool two = e->cfg.passes == 2;
     const bool mode2 = two && e->cfg.two_pass_mode == 2;
@@ -330,7 +341,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         p.out = out_y; p.out_pitch = out_step; p.W = e->out_w; p.H = e->out_h; p.row0 = row0; p.row1 = row1;
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
-        p.band_done = band_done;
+        p.band_done = band_done; p.out_tail = out_tail; p.out_tail_pitch = out_tail_step;
         p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_band_rows = in_band_rows;
         return launch_pass(e, p, s);
     }
@@ -356,7 +367,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = row0; p2.row1 = row1;
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
-    p2.band_done = band_done;
+    p2.band_done = band_done; p2.out_tail = out_tail; p2.out_tail_pitch = out_tail_step;
     p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows;
     set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
     int rc = launch_pass(e, p1, s);
@@ -726,14 +737,18 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     } else if (band_d2h) {
         // The final pass counts finished tiles per row band (running totals, never reset); the D2H stream waits on each counter
         // and copies that band while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows, cjp);
+        const void *tail_dev = nullptr;                                     // rows of the last round of tiles: in place when the plane is pinned
+        const bool tail_direct = (e->zero_copy & 4) && mapped_host_pointer(out_y, &tail_dev);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows, cjp,
+                          tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step);
         if (rc) return rc;
         if (e->timing) cudaEventRecord(e->tev[2], e->stream);
         if ((rc = after_launch())) return rc;
         const int gx = (e->out_w + TW - 1) / TW;
-        const int bty = (e->last_grid_y + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands;
-        for (int b = 0, ty = 0; ty < e->last_grid_y; ++b, ty += bty) {
-            const int tiles_y = std::min(bty, e->last_grid_y - ty);
+        const int nrows_b = e->last_banded_rows;
+        const int bty = std::max(1, (nrows_b + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands);
+        for (int b = 0, ty = 0; ty < nrows_b; ++b, ty += bty) {
+            const int tiles_y = std::min(bty, nrows_b - ty);
             const int r0 = ty * e->last_tile_h, r1 = std::min(e->out_h, (ty + tiles_y) * e->last_tile_h);
             e->band_target[b] += (unsigned)(tiles_y * gx);
             if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), e->band_target[b], 0 /* GEQ */) != 0)

@@ -49,6 +49,9 @@ struct PassParams {
     int in_band_rows;        // input rows per band
     unsigned *band_done;     // optional: per row band, the number of finished tiles (host-side copy pipeline)
     int band_tiles_y;        // tile rows per band
+    void *out_tail;          // optional: output rows >= tail_row0 go here instead (the caller's pinned plane, written in place:
+    size_t out_tail_pitch;   //           the rows of the last round of tiles need no copy after the kernel); not counted in band_done
+    int tail_row0;
     float qstr0, qstr1, qcoh0, qcoh1;
     int lo, hi;              // colour range
     int c_end;               // hashed columns are [6, c_end)                  (Raisr.cpp:1065-1066)
@@ -500,7 +503,8 @@ __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const f
             }
             iv[e] = r;
         }
-        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out) + (size_t)Y * p.out_pitch) + X;
+        const bool tail = p.out_tail != nullptr && Y >= p.tail_row0;
+        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(tail ? p.out_tail : p.out) + (size_t)Y * (tail ? p.out_tail_pitch : p.out_pitch)) + X;
         if (p.vec_store && X + 3 < W) {
             if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = (uint32_t)iv[0] | ((uint32_t)iv[1] << 8) | ((uint32_t)iv[2] << 16) | ((uint32_t)iv[3] << 24);
             else *reinterpret_cast<uint2 *>(orow) = make_uint2((uint32_t)iv[0] | ((uint32_t)iv[1] << 16), (uint32_t)iv[2] | ((uint32_t)iv[3] << 16));

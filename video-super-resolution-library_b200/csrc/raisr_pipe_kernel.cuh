@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
             group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
             if (tile + 2 * (int)gridDim.x < ntiles) named_arrive(BAR_EMPTY + buf, NBT + NCT);   // bucket tile may be refilled (tile i+2)
-            if (p.band_done && ct == 0) {
+            if (p.band_done && ct == 0 && !(p.out_tail && y0 >= p.tail_row0)) {
                 __threadfence();
                 atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
             }
