@@ -122,6 +122,7 @@ struct raisr_cuda_engine {
     int device = 0;
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
+    bool split_h2d = true;          // pipelined kernel: input plane in two copies, the second one under the kernel; RAISR_CUDA_SPLIT_H2D=0 disables
     int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
     int zero_copy = 4;              // bit 2: write the rows of the last round of tiles straight into a pinned output plane (no copy after the kernel), bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
     int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
@@ -330,7 +331,7 @@ void set_chroma(const raisr_cuda_engine *e, const ChromaJob *c, PassParams *p)
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
              cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0,
-             const ChromaJob *chroma = nullptr, void *out_tail = nullptr, size_t out_tail_step = 0)
+             const ChromaJob *chroma = nullptr, void *out_tail = nullptr, size_t out_tail_step = 0, int in_split_row = 0)
 {
     const bool two = e->cfg.passes == 2;
     const bool mode2 = two && e->cfg.two_pass_mode == 2;
@@ -342,7 +343,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
         p.band_done = band_done; p.out_tail = out_tail; p.out_tail_pitch = out_tail_step;
-        p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_band_rows = in_band_rows;
+        p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_band_rows = in_band_rows; p.in_split_row = in_split_row;
         return launch_pass(e, p, s);
     }
     // Two passes on a row band: pass 1 is recomputed on the rows pass 2 can reach (+-7 output rows of pass 2, mapped back
@@ -368,7 +369,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
     p2.band_done = band_done; p2.out_tail = out_tail; p2.out_tail_pitch = out_tail_step;
-    p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows;
+    p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows; p1.in_split_row = in_split_row;
     set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
     int rc = launch_pass(e, p1, s);
     if (rc) return rc;
@@ -455,6 +456,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
     if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
     if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
+    if (const char *sp = std::getenv("RAISR_CUDA_SPLIT_H2D")) e->split_h2d = std::atoi(sp) != 0;
     if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
     if (std::getenv("RAISR_CUDA_TIMING")) { e->timing = true; for (auto &ev : e->tev) cudaEventCreate(&ev); }
@@ -648,17 +650,35 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     const bool in_direct = (e->zero_copy & 1) && mapped_host_pointer(in_y, &k_in);
     if (in_direct) k_in_step = in_y_step;
     const unsigned *in_ready = nullptr;
-    int in_band_rows = 0;
+    int in_band_rows = 0, split_row = 0;
     const bool banded_h2d = !in_direct && e->h2d_bands > 1 && memops && !e->use_pipe;   // (the pipelined kernel: measured no gain, costs registers)
     if (banded_h2d) {
         ++e->frame_seq;
         in_band_rows = (e->in_h + e->h2d_bands - 1) / e->h2d_bands;
         in_ready = e->d_in_ready;
     } else if (!in_direct) {
+        // Pipelined kernel: only the input rows the first tiles read are copied ahead of the launch; the rest follows on the H2D
+        // stream while the kernel works on those tiles, flagged to the chain warps (RAISR_CUDA_SPLIT_H2D=0: one copy).
+        if (e->use_pipe && memops && e->split_h2d && e->in_h >= 256) {
+            split_row = std::max(64, (e->in_h / 8 + 15) & ~15);
+            ++e->frame_seq;
+            in_ready = e->d_in_ready;
+        }
+        const int rows0 = split_row ? split_row : e->in_h;
         if (e->timing) cudaEventRecord(e->tev[0], e->stream);
-        CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+        CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, rows0, cudaMemcpyHostToDevice, e->stream));
         if (e->timing) cudaEventRecord(e->tev[1], e->stream);
-        if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream));   // the chroma copies queue up behind the luma copy (same copy engine)
+        if (split_row) {
+            CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));                  // part 2 behind part 1 (same copy engine anyway)
+            CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
+                                      static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
+                                      cudaMemcpyHostToDevice, e->stream_h2d));
+            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+            if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));   // the chroma copies queue up behind the luma copies
+        } else if (fused) {
+            CUDA_OK(cudaEventRecord(e->ev_in, e->stream));                  // the chroma copies queue up behind the luma copy (same copy engine)
+        }
     }
 
     // ---- chroma job of the pipelined kernel -----------------------------------------------------------------------------
@@ -729,7 +749,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     const bool band_d2h = !out_direct && memops && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
     if (out_direct) {
         // pinned caller plane written in place by the final pass (small PCIe writes from the SMs, spread over the kernel)
-        int rc = run_luma(e, k_in, k_in_step, const_cast<void *>(out_dev), out_y_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp);
+        int rc = run_luma(e, k_in, k_in_step, const_cast<void *>(out_dev), out_y_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp, nullptr, 0, split_row);
         if (rc) return rc;
         if (e->timing) cudaEventRecord(e->tev[2], e->stream);
         if ((rc = after_launch())) return rc;
@@ -740,7 +760,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         const void *tail_dev = nullptr;                                     // rows of the last round of tiles: in place when the plane is pinned
         const bool tail_direct = (e->zero_copy & 4) && mapped_host_pointer(out_y, &tail_dev);
         int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows, cjp,
-                          tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step);
+                          tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step, split_row);
         if (rc) return rc;
         if (e->timing) cudaEventRecord(e->tev[2], e->stream);
         if ((rc = after_launch())) return rc;
@@ -760,13 +780,13 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
         CUDA_OK(cudaStreamSynchronize(e->stream));
     } else {
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp);
+        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp, nullptr, 0, split_row);
         if (rc) return rc;
         CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
         if ((rc = after_launch())) return rc;
         CUDA_OK(cudaStreamSynchronize(e->stream));
     }
-    if (banded_h2d) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
+    if (banded_h2d || split_row) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
     if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
     if (e->timing && !in_direct && !banded_h2d) {
         float a = 0, b = 0;

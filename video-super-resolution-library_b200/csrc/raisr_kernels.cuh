@@ -47,6 +47,7 @@ struct PassParams {
     const unsigned *in_ready; // optional: per input row band, the frame sequence number once its H2D copy has landed
     unsigned in_seq;         // sequence number of this frame
     int in_band_rows;        // input rows per band
+    int in_split_row;        // pipelined kernel: input rows >= in_split_row are valid once *in_ready == in_seq (rows above: stream order)
     unsigned *band_done;     // optional: per row band, the number of finished tiles (host-side copy pipeline)
     int band_tiles_y;        // tile rows per band
     void *out_tail;          // optional: output rows >= tail_row0 go here instead (the caller's pinned plane, written in place:

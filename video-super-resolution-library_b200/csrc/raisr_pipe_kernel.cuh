@@ -94,11 +94,40 @@ __device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
     return load_S<PixT>(p, Yc, Xc, UPS != 0);
 }
 
+// Split H2D: the lower part of the input plane (rows >= in_split_row) may still be on its way (own stream, flagged).  Called by
+// the chain warps before the ring fill of the first tile that reads such rows.  Not inlined, scalar arguments only (taking the
+// address of the kernel parameter block would move every access to it into local memory).
+__device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, int lt)
+{
+    if (lt == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v != seq);
+    }
+    group_sync(BAR_CHAIN, NBT);
+}
+
 // Chroma planes: plain cheap upscale (Raisr.cpp:1373-1388) of this CTA's share of the planes, slice sl of nslices, by the filter
 // warps (NCT threads, ct = thread index in the group).  Not inlined: keeps its registers out of the filter loop's allocation.
+struct ChromaParams {
+    int chroma_n;
+    const void *in[2]; size_t in_pitch[2]; void *out[2]; size_t out_pitch[2];
+    int c_in_w, c_in_h, c_W, c_H;
+    const int *c_xmap, *c_xw, *c_ymap, *c_yw;
+    int c_denx, c_deny;
+    const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done;
+};
 template <typename PixT>
-__device__ __noinline__ void chroma_slice_fn(const PassParams &p, int sl, int nslices, int ct)
+__device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int nslices, int ct)
 {
+    struct { int chroma_n; struct { const void *in; size_t in_pitch; void *out; size_t out_pitch; } chroma[2]; int c_in_w, c_in_h, c_W, c_H;
+             const int *c_xmap, *c_xw, *c_ymap, *c_yw; int c_denx, c_deny; const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done; } p;
+    p.chroma_n = cp.chroma_n;
+    for (int i = 0; i < 2; ++i) { p.chroma[i].in = cp.in[i]; p.chroma[i].in_pitch = cp.in_pitch[i]; p.chroma[i].out = cp.out[i]; p.chroma[i].out_pitch = cp.out_pitch[i]; }
+    p.c_in_w = cp.c_in_w; p.c_in_h = cp.c_in_h; p.c_W = cp.c_W; p.c_H = cp.c_H;
+    p.c_xmap = cp.c_xmap; p.c_xw = cp.c_xw; p.c_ymap = cp.c_ymap; p.c_yw = cp.c_yw; p.c_denx = cp.c_denx; p.c_deny = cp.c_deny;
+    p.chroma_ready = cp.chroma_ready; p.chroma_seq = cp.chroma_seq; p.chroma_done = cp.chroma_done;
     if (sl == 0 && p.chroma_ready) {                                 // the planes' H2D copies run on their own stream
         if (ct == 0) {
             unsigned v;
@@ -262,6 +291,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         // across tile boundaries, where the chain warps refill the ring while the bucket warps finish the previous tile.
         int iter = 0;
         unsigned gk = 0;                                                     // running chunk number
+        bool input_complete = false;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
             unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
@@ -341,6 +371,16 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             };
             const int nchunks = hh / RBP;
             if (chain_warp) {
+                // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Only the chain warps
+                // look: the filter warps work on a tile the chain warps have already seen, and tiles come in row order.
+                if (p.in_ready && !input_complete) {
+                    const int ylast = min(H - 1, y0 + th + 6);
+                    const int in_last = (UPS == 0) ? ylast : (UPS == 1) ? (ylast >> 1) + 1 : (__ldg(p.ymap + ylast) >> 1) + 1;
+                    if (in_last >= p.in_split_row) {
+                        wait_split_input(p.in_ready, p.in_seq, lt);
+                        input_complete = true;
+                    }
+                }
                 // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1)
                 // reads rows 2k .. 2k+13.  Rows 0 .. 13 up front (the previous tile's last B is done: BAR_PROD), every chunk then
                 // fetches the two rows of the NEXT chunk into the slots of rows 2k-2, 2k-1.
@@ -423,7 +463,15 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         const int cta_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         const int nslices = min(3, max(1, cta_tiles - 1));                   // early in the frame: the host may copy the planes out while the luma runs on
         int slices_done = 0;
-        auto chroma_slice = [&](int sl) { chroma_slice_fn<PixT>(p, sl, nslices, ct); };
+        auto chroma_slice = [&](int sl) {                                 // by value: never take the address of the kernel parameter block
+            ChromaParams cp;
+            cp.chroma_n = p.chroma_n;
+            for (int i = 0; i < 2; ++i) { cp.in[i] = p.chroma[i].in; cp.in_pitch[i] = p.chroma[i].in_pitch; cp.out[i] = p.chroma[i].out; cp.out_pitch[i] = p.chroma[i].out_pitch; }
+            cp.c_in_w = p.c_in_w; cp.c_in_h = p.c_in_h; cp.c_W = p.c_W; cp.c_H = p.c_H;
+            cp.c_xmap = p.c_xmap; cp.c_xw = p.c_xw; cp.c_ymap = p.c_ymap; cp.c_yw = p.c_yw; cp.c_denx = p.c_denx; cp.c_deny = p.c_deny;
+            cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done;
+            chroma_slice_fn<PixT>(cp, sl, nslices, ct);
+        };
         unsigned nload = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
