@@ -187,14 +187,15 @@ def test_full_size_properties_4k():
     eng.close()
 
 
-def test_pipelined_kernel_variant_is_bit_identical(monkeypatch):
-    """RAISR_CUDA_KERNEL=pipe (persistent warp-specialised schedule) must give exactly the default kernel's output."""
+def test_phase_sequential_kernel_variant_is_bit_identical(monkeypatch):
+    """RAISR_CUDA_KERNEL=tile (phase-sequential schedule) must give exactly the default (pipelined, warp-specialised) kernel's
+    buckets and pixels."""
     f = T.filter_folder("filters_2x/filters_highres")
     img = T.synth_frame(500, 300, 8, seed=31, kind="mix")
     base, hb = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
-    monkeypatch.setenv("RAISR_CUDA_KERNEL", "pipe")
-    pipe, hp = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
-    assert np.array_equal(base, pipe) and all(np.array_equal(a, b) for a, b in zip(hb, hp))
+    monkeypatch.setenv("RAISR_CUDA_KERNEL", "tile")
+    tile, ht = run_engine(f, img, 2.0, 8, 2, 1, numerics=B.NUMERICS_AUTO)
+    assert np.array_equal(base, tile) and all(np.array_equal(a, b) for a, b in zip(hb, ht))
 
 
 @pytest.mark.parametrize("numerics", [B.NUMERICS_IEEE, B.NUMERICS_X86])
