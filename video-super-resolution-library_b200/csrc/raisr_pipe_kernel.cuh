@@ -251,14 +251,9 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
 
     HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
 
-    // warps [0, NCW) are consumers, warps [NCW, NCW + NPW) producers (PIPE_PROD_FIRST: the other way round)
-#ifdef PIPE_PROD_FIRST
-    const bool is_prod = tid0 < NPT;
-    const int tid = tid0, ct = tid0 - NPT;
-#else
+    // warps [0, NCW) are the filter warps, warps [NCW, NCW + NPW) the producers (bucket warps, then chain warps)
     const bool is_prod = tid0 >= NCT;
     const int tid = tid0 - NCT, ct = tid0;
-#endif
     if (is_prod) {
         // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));   // hand registers to the consumer warpgroups
@@ -525,11 +520,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
 
             // ---- D: 121-tap filter, one pixel type at a time ----
             const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
-#ifdef PIPE_DBG_SKIP_D
-            for (int t = 0; t < 0; ++t) {
-#else
             for (int t = 0; t < PT; ++t) {
-#endif
                 if (ct == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(mslice, (unsigned)slice_bytes);
