@@ -346,7 +346,20 @@ def main():
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                tj = json.load(open(traffic_file))
+                line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                # the resources that actually bound the kernel: per-launch counts from the committed ncu
+                # capture, rates from this run's kernel time and the SM clock sampled during the timed region
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                sms = torch.cuda.get_device_properties(local).multi_processor_count
+                wf, wi = tj.get("smem_wavefronts_per_launch"), tj.get("warp_instructions_per_launch")
+                if wf and wi:
+                    line["roofline"]["onchip"] = {
+                        "shared_memory_pipe": {"wavefronts_per_launch": wf, "peak_per_s": sms * mhz * 1e6,
+                                               "frac": wf / (kern_ms * 1e-3) / (sms * mhz * 1e6)},
+                        "issue_slots": {"warp_instructions_per_launch": wi, "peak_per_s": 4 * sms * mhz * 1e6,
+                                        "frac": wi / (kern_ms * 1e-3) / (4 * sms * mhz * 1e6)},
+                        "source": tj.get("source")}
             except Exception:
                 pass
         print(json.dumps(line))
