@@ -341,7 +341,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_Y,
                          "note": "compute-bound stencil: fp32 issue + shared-memory gather, see DESIGN.md"},
-            "cpu_baseline": cpu_baseline_leg(),
+            "cpu_baseline": cpu_baseline_leg() if world == 1 else None,      # timed at N=1 only
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):

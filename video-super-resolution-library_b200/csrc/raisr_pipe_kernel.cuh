@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         // cut into up to three slices, one per tile from the second tile on, done while the filter warps would otherwise wait for
         // the bucket tile: no launch of its own, and finished early enough for the host to copy the planes out under the kernel.
         const int cta_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-        const int nslices = min(3, max(1, cta_tiles - 1));                   // early in the frame: the host may copy the planes out while the luma runs on
+        const int nslices = min(3, max(1, cta_tiles - 2));                   // early in the frame: the host may copy the planes out while the luma runs on
         int slices_done = 0;
         auto chroma_slice = [&](int sl) {                                 // by value: never take the address of the kernel parameter block
             ChromaParams cp;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int h = idx / HW, j = idx - h * HW;
                 sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
             }
-            if (p.chroma_n > 0 && iter >= 1 && slices_done < nslices) chroma_slice(slices_done++);
+            if (p.chroma_n > 0 && iter >= 2 && slices_done < nslices) chroma_slice(slices_done++);
             group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
             group_sync(BAR_FULL + buf, NBT + NCT);                            // buckets of this tile are ready
 
