@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
         const unsigned fbase = smem_u32(sF) + 16u * (unsigned)q;          // this lane's 16 bytes of every 128-byte filter step
         const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
         // ---- chroma planes: plain cheap upscale (Raisr.cpp:1373-1388), 4 pixels per thread.  This CTA's share of the planes is
-        // cut into up to three slices, one per tile from the second tile on, done while the filter warps would otherwise wait for
+        // cut into up to three slices, one per tile from the third tile on (the planes' H2D copies have landed by then), done while the filter warps would otherwise wait for
         // the bucket tile: no launch of its own, and finished early enough for the host to copy the planes out under the kernel.
         const int cta_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         const int nslices = min(3, max(1, cta_tiles - 2));                   // early in the frame: the host may copy the planes out while the luma runs on
