@@ -46,7 +46,7 @@ constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;           // 2 
 constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * 2 * QCHUNK;          // filter-slice mbarrier
 constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(float) * (((PTH_MAX + 14) / 2 + 1) * LRP) <= sizeof(float) * SLICE_FLOATS, "low-res staging fits in the slice buffer");
+static_assert(((PTH_MAX + 14) / 2 + 1) * LRP <= PHH * HP, "low-res staging fits in the HR tile");
 
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             chroma_slice_fn<PixT>(cp, sl, nslices, ct);
         };
         unsigned nload = 0;
+        int resident_type = -1;                                           // pixel type whose filter slice is in shared memory
         int iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
@@ -476,9 +477,10 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
 
-            // ---- A: S tile (the slice buffer is free until the first slice load: low-res staging for the 2x path) ----
+            // ---- A: S tile (the HR tile is free until the HR := S copy below: low-res staging for the 2x path; the slice buffer
+            // keeps the previous tile's last filter slice) ----
             if (UPS == 1) {
-                float *sL = sF;
+                float *sL = sHR;
                 const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;
                 const int lrh = (th + 14) / 2 + 1;
                 for (int idx = ct; idx < lrh * LRW; idx += NCT) {
@@ -520,8 +522,11 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
 
             // ---- D: 121-tap filter, one pixel type at a time ----
             const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
-            for (int t = 0; t < PT; ++t) {
-                if (ct == 0) {
+            // pixel types in alternating order (0..PT-1, then PT-1..0): the slice the previous tile ended with is still resident
+            for (int ti = 0; ti < PT; ++ti) {
+                const int t = (iter & 1) ? PT - 1 - ti : ti;
+                const bool load = t != resident_type;
+                if (load && ct == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(mslice, (unsigned)slice_bytes);
                     const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
@@ -531,8 +536,11 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;
                 const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
                 const int nrows = (hh - hfirst + JS - 1) / JS;
-                mbar_wait(mslice, nload & 1u);
-                ++nload;
+                if (load) {
+                    mbar_wait(mslice, nload & 1u);
+                    ++nload;
+                    resident_type = t;
+                }
                 // One warp iteration = UU groups of 4 pixels of one tile row: addresses = per-lane constant + uniform + immediate,
                 // packed FMUL2/FFMA2 for the chain pair (2q, 2q+1), and the 16 -> 1 lane tree of the 4 pixel groups folded into 8 shuffles:
                 // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
