@@ -82,7 +82,8 @@ def test_pinned_and_pageable_planes_give_the_same_frame(cfg, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"RAISR_CUDA_SPLIT_H2D": "0"}, {"RAISR_CUDA_ZERO_COPY": "0"}, {"RAISR_CUDA_ZERO_COPY": "2"},
-                                 {"RAISR_CUDA_ZERO_COPY": "7"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}, {"RAISR_CUDA_KERNEL": "tile"}],
+                                 {"RAISR_CUDA_ZERO_COPY": "7"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}, {"RAISR_CUDA_KERNEL": "tile"},
+                                 {"RAISR_CUDA_NO_MEMOPS": "1"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_copy_strategies_are_invisible(env, monkeypatch):
     cfg = CONFIGS[1]

@@ -122,6 +122,7 @@ struct raisr_cuda_engine {
     int device = 0;
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
+    bool no_memops = false;         // RAISR_CUDA_NO_MEMOPS=1 (or CUDA_LAUNCH_BLOCKING=1): no in-kernel flag waits, everything in plain stream order
     bool split_h2d = true;          // pipelined kernel: input plane in two copies, the second one under the kernel; RAISR_CUDA_SPLIT_H2D=0 disables
     int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
     int zero_copy = 4;              // bit 2: write the rows of the last round of tiles straight into a pinned output plane (no copy after the kernel), bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
@@ -457,6 +458,8 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
     if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
     if (const char *sp = std::getenv("RAISR_CUDA_SPLIT_H2D")) e->split_h2d = std::atoi(sp) != 0;
+    if (const char *nm = std::getenv("RAISR_CUDA_NO_MEMOPS")) e->no_memops = std::atoi(nm) != 0;
+    if (const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING")) e->no_memops = e->no_memops || std::atoi(lb) != 0;
     if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
     if (std::getenv("RAISR_CUDA_TIMING")) { e->timing = true; for (auto &ev : e->tev) cudaEventCreate(&ev); }
@@ -620,7 +623,10 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     CUDA_OK(cudaSetDevice(e->device));
     const size_t bps = e->bps;
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
-    const bool memops = e->wait_value32 && e->write_value32;       // stream memory operations (cuStreamWaitValue32 / WriteValue32)
+    // stream memory operations (cuStreamWaitValue32 / WriteValue32) let copies run under the kernel, which then waits in-kernel for
+    // flags.  That needs copies and kernel to make progress concurrently: tools that serialise the GPU (compute-sanitizer,
+    // CUDA_LAUNCH_BLOCKING=1) must use the plain stream-ordered pipeline (RAISR_CUDA_NO_MEMOPS=1, implied by CUDA_LAUNCH_BLOCKING).
+    const bool memops = e->wait_value32 && e->write_value32 && !e->no_memops;
     auto memop_failed = [](const char *what) { std::cout << "[RAISR ERROR] " << what << " failed" << std::endl; return (int)RNLErrorUndefined; };
     // Pipelined kernel: the chroma planes are resized by the luma launch itself (its filter warps, early in the frame, while
     // they would otherwise wait for the first bucket tiles); only the copies remain here.  Phase-sequential kernel: chroma on
@@ -692,6 +698,16 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
         if (memops) {
             cj.ready = e->d_chroma_ready; cj.seq = ++e->chroma_seq;          // H2D on the chroma stream, flagged to the running kernel
             cj.done = e->d_chroma_ready + 1; chroma_early_d2h = true;        // D2H by the copy engine as soon as every CTA has written its share
+            if (!banded_h2d) {
+                // everything the kernel will wait for is enqueued BEFORE the launch (a blocking launch cannot starve it)
+                const void *src[2] = {in_u, in_v};
+                const size_t sstep[2] = {in_u_step, in_v_step};
+                if (!in_direct) CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
+                for (int i = 0; i < 2; ++i)
+                    CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                              cudaMemcpyHostToDevice, e->stream_uv));
+                if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+            }
         } else {
             const void *src[2] = {in_u, in_v};
             const size_t sstep[2] = {in_u_step, in_v_step};
@@ -722,13 +738,15 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
                                           cudaMemcpyDeviceToHost, e->stream));
             return 0;
         }
-        const void *src[2] = {in_u, in_v};
-        const size_t sstep[2] = {in_u_step, in_v_step};
-        if (!in_direct) CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
-        for (int i = 0; i < 2; ++i)
-            CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
-                                      cudaMemcpyHostToDevice, e->stream_uv));
-        if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+        if (banded_h2d) {                                                    // (phase-sequential kernel only: no fused chroma, kept for symmetry)
+            const void *src[2] = {in_u, in_v};
+            const size_t sstep[2] = {in_u_step, in_v_step};
+            CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
+            for (int i = 0; i < 2; ++i)
+                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                          cudaMemcpyHostToDevice, e->stream_uv));
+            if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+        }
         e->chroma_done_target += (unsigned)e->last_grid_x;                   // running total: no reset, no race with the previous frame
         if (e->wait_value32(e->stream_uv, (unsigned long long)(uintptr_t)(e->d_chroma_ready + 1), e->chroma_done_target, 0 /* GEQ */) != 0)
             return memop_failed("cuStreamWaitValue32");
