@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                 // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
                 // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
                 const unsigned hbase = smem_u32(sHash) + (unsigned)(g * JS);
+                const unsigned lastrow = (unsigned)p.nbuckets - 1u;
                 auto fast_block = [&](auto uu, const int h, const int jc0) {   // h, jc0 (block column 0) are warp-uniform
                     constexpr int UU = decltype(uu)::value;
                     const unsigned ub = 4u * (unsigned)(h * SP + jc0);
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     hv[0] = lds_u8<0>(hva); hv[1] = lds_u8<4 * JS>(hva);
                     hv[2] = (UU > 2) ? lds_u8<8 * JS>(hva) : 255u; hv[3] = (UU > 3) ? lds_u8<12 * JS>(hva) : 255u;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) fa[u] = fbase + (hv[u] << 9);     // 255 (not hashed): some in-bounds garbage row, result dropped
+                    for (int u = 0; u < 4; ++u) fa[u] = fbase + (min(hv[u], lastrow) << 9);   // 255 (not hashed): any row of the slice, result dropped
                     f32x2 acc[4];
                     auto step = [&](auto nn) {
                         constexpr int n = decltype(nn)::value;
