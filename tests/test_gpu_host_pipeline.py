@@ -24,6 +24,8 @@ CONFIGS = [
     ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (480, 270)),      # 16-bit samples, pass 1 at input resolution
     ("filters_1.5x/filters_highres", 1.5, 8, 1, 1, (640, 360)),     # generic-ratio chroma path inside the kernel
     ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (150, 66)),         # fewer tiles than SMs: chroma slices after the tile loop
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (333, 190)),        # odd sizes: no vector stores, every tile row written in place when pinned, chroma ratio != 2
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1, (1000, 600)),      # several rounds of tiles: some rows band-copied, the last ones in place
 ]
 
 
@@ -43,7 +45,7 @@ def run_host(cfg, src, pinned, env=None, monkeypatch=None):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
     eng = B.Engine(T.filter_folder(folder), ratio, bits, T.VideoRange, passes, mode, numerics=B.NUMERICS_AUTO)
-    eng.set_res(w, h, oW, oH, w // 2, h // 2, oW // 2, oH // 2)
+    eng.set_res(w, h, oW, oH, w // 2, h // 2, oW // 2, oH // 2)       # (odd sizes: chroma ratio is not exactly the luma ratio)
     dt = src[0].dtype
     outs = [np.zeros((oH, oW), dt), np.zeros((oH // 2, oW // 2), dt), np.zeros((oH // 2, oW // 2), dt)]
     ins = list(src)
