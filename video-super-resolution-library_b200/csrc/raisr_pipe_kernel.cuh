@@ -12,8 +12,8 @@
 // warps hand over a pair of bucket tiles guarded by hardware named barriers (bar.arrive / bar.sync, full and empty per
 // tile buffer: the waiting side blocks without consuming issue slots).
 //
-// Register file: the CTA is launched with 72 registers per thread; the producer warpgroups drop to 56 and the filter
-// warpgroups rise to 88 (setmaxnreg).  The upscaled rows of chunk k+2 are fetched from global memory before the barrier
+// Register file: the CTA is launched with 72 registers per thread; the chain warpgroups drop to 48, the bucket warpgroups to
+// 64 and the filter warpgroups rise to 88 (setmaxnreg).  The upscaled rows of chunk k+2 are fetched from global memory before the barrier
 // of chunk k and stored into free ring slots after stage B (latency hidden).
 //
 // STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite, tools/kbench.py); 0.63 ms vs 0.85 ms per 4K frame.
@@ -27,7 +27,8 @@ constexpr int NPW = 16;                      // producer warps: 8 chain warps (s
 constexpr int NCW = NTP / 32 - NPW;          // filter (consumer) warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
 constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
-constexpr int PROD_REGS = 56, CONS_REGS = 88;    // setmaxnreg targets: 512*56 + 384*88 <= 896*72 registers of the CTA (measured: 48/104 0.615 ms, 56/88 0.606 ms, 64/80 0.615 ms)
+constexpr int CHAIN_REGS = 48, BUCKET_REGS = 64, CONS_REGS = 88;   // setmaxnreg targets: 256*48 + 256*64 + 384*88 <= 896*72 registers of the CTA
+                                                                   // (measured: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms)
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
 static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
@@ -256,7 +257,9 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
     const int tid = tid0 - NCT, ct = tid0;
     if (is_prod) {
         // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));   // hand registers to the consumer warpgroups
+        // hand registers to the filter warpgroups; the chain warps (18 accumulators) need fewer than the hash
+        if (tid >= NBT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BUCKET_REGS));
         // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
         // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
         // columns sx = 2t, 2t+1.  Split into load and store so that the global-memory latency hides behind stage B.
