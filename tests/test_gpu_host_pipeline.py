@@ -83,9 +83,8 @@ def test_pinned_and_pageable_planes_give_the_same_frame(cfg, monkeypatch):
     assert np.array_equal(base[1], T.oracle_resize(src[1], oW, oH)) and np.array_equal(base[2], T.oracle_resize(src[2], oW, oH))
 
 
-@pytest.mark.parametrize("env", [{"RAISR_CUDA_SPLIT_H2D": "0"}, {"RAISR_CUDA_ZERO_COPY": "0"}, {"RAISR_CUDA_ZERO_COPY": "2"},
-                                 {"RAISR_CUDA_ZERO_COPY": "7"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}, {"RAISR_CUDA_KERNEL": "tile"},
-                                 {"RAISR_CUDA_NO_MEMOPS": "1"}],
+@pytest.mark.parametrize("env", [{"RAISR_CUDA_SPLIT_H2D": "0"}, {"RAISR_CUDA_TAIL_IN_PLACE": "0"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"},
+                                 {"RAISR_CUDA_KERNEL": "tile"}, {"RAISR_CUDA_NO_MEMOPS": "1"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_copy_strategies_are_invisible(env, monkeypatch):
     cfg = CONFIGS[1]
@@ -117,3 +116,95 @@ def test_device_entry_with_chroma_equals_host_entry():
     for a, b, n in zip(host, d_out, "YUV"):
         assert np.array_equal(a, b.cpu().numpy()), n
     eng.close()
+
+
+# ---- hazards of the host engine (round-1 review): counters that start at zero, state that is per engine, races of the split H2D ----
+def _pin(a, keep):
+    import torch
+    t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).clone().pin_memory()
+    keep.append(t)
+    return t.numpy().view(a.dtype)
+
+
+def test_many_create_destroy_cycles_with_the_band_pipeline():
+    """200 engines in one process on page-locked planes: every engine's band / chroma / input counters must start from zero
+    (recycled device allocations are not zeroed by cudaMalloc), or a band is copied out before it is computed."""
+    cfg = CONFIGS[6]
+    folder, ratio, bits, passes, mode, (w, h) = cfg
+    src = planes(w, h, bits, seed=21)
+    want = run_host(cfg, src, pinned=False)
+    keep = []
+    ins = [_pin(a, keep) for a in src]
+    oW, oH = int(w * ratio), int(h * ratio)
+    outs = [_pin(np.zeros((oH, oW), np.uint8), keep), _pin(np.zeros((oH // 2, oW // 2), np.uint8), keep),
+            _pin(np.zeros((oH // 2, oW // 2), np.uint8), keep)]
+    for cycle in range(200):
+        eng = B.Engine(T.filter_folder(folder), ratio, bits, T.VideoRange, passes, mode, numerics=B.NUMERICS_AUTO)
+        eng.set_res(w, h, oW, oH, w // 2, h // 2, oW // 2, oH // 2)
+        for o in outs:
+            o[...] = 0
+        assert eng.process_host(ins[0], outs[0], ins[1], ins[2], outs[1], outs[2]) == 0
+        eng.close()
+        for a, b, n in zip(want, outs, "YUV"):
+            assert np.array_equal(a, b), "cycle %d: %s plane differs on %d samples" % (cycle, n, (a != b).sum())
+
+
+def test_two_live_engines_with_different_bit_depths_interleaved():
+    """An 8-bit and a 10-bit engine alive on one device, frames interleaved: the Gaussian weights (bit-depth dependent
+    normalisation, Raisr_globals.h:204-206) are per launch, not process-global device state."""
+    f8, f10 = T.filter_folder("filters_2x/filters_lowres"), T.filter_folder("filters_2x/filters_highres")
+    w, h = 322, 182
+    i8, i10 = T.synth_frame(w, h, 8, seed=31), T.synth_frame(w, h, 10, seed=32, kind="edges")
+    ref8 = T.oracle_process_y(i8, 2 * w, 2 * h, T.OracleModel(f8, 8))
+    ref10 = T.oracle_process_y(i10, 2 * w, 2 * h, T.OracleModel(f10, 10))
+    e8 = B.Engine(f8, 2.0, 8, T.VideoRange, 1, 1, numerics=B.NUMERICS_IEEE)
+    e10 = B.Engine(f10, 2.0, 10, T.VideoRange, 1, 1, numerics=B.NUMERICS_IEEE)     # created second: would overwrite shared weights
+    e8.set_res(w, h, 2 * w, 2 * h)
+    e10.set_res(w, h, 2 * w, 2 * h)
+    for _ in range(3):
+        o8, o10 = np.zeros((2 * h, 2 * w), np.uint8), np.zeros((2 * h, 2 * w), np.uint16)
+        assert e8.process_host(i8, o8) == 0
+        assert e10.process_host(i10, o10) == 0
+        assert np.array_equal(o8, ref8), "8-bit engine: %d px differ" % (o8 != ref8).sum()
+        assert np.array_equal(o10, ref10), "10-bit engine: %d px differ" % (o10 != ref10).sum()
+    e8.close()
+    e10.close()
+
+
+@pytest.mark.parametrize("size", [(96, 256), (128, 300), (640, 512)], ids=lambda s: "%dx%d" % s)
+def test_split_h2d_on_small_tall_frames_with_pinned_planes(size):
+    """in_h >= 256 with fewer tiles than SMs: every tile is a CTA's first, so the filter warps read input rows behind the split
+    at kernel start -- they must be ordered behind the flag the H2D stream writes (page-locked planes make the copy truly async)."""
+    w, h = size
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = T.synth_frame(w, h, 8, seed=w + h, kind="noise")
+    ref = T.oracle_process_y(img, 2 * w, 2 * h, T.OracleModel(f, 8))
+    keep = []
+    pin_in, pin_out = _pin(img, keep), _pin(np.zeros((2 * h, 2 * w), np.uint8), keep)
+    eng = B.Engine(f, 2.0, 8, T.VideoRange, 1, 1, numerics=B.NUMERICS_IEEE)
+    eng.set_res(w, h, 2 * w, 2 * h)
+    for k in range(20):
+        pin_in[...] = 0 if k % 2 else img                     # alternate with a blank frame: stale rows would show
+        pin_out[...] = 0
+        assert eng.process_host(pin_in, pin_out) == 0
+        if k % 2 == 0:
+            assert np.array_equal(pin_out, ref), "frame %d: %d px differ" % (k, (pin_out != ref).sum())
+    eng.close()
+
+
+def test_setres_rejects_cb_geometry_that_differs_from_cr():
+    import ctypes as C
+    L = T.handler_lib(T.product_lib_path())
+    f = T.filter_folder("filters_2x/filters_lowres")
+    y, u, v = planes(64, 48, 8, seed=3)
+    oy, ou, ov = np.zeros((96, 128), np.uint8), np.zeros((48, 64), np.uint8), np.zeros((48, 64), np.uint8)
+    assert L.RNLHandler_Init(f.encode(), 2.0, 8, T.VideoRange, 1, T.AVX512, 1, 1) == 0
+    try:
+        good = [T.vdt(a) for a in (y, u, v, oy, ou, ov)]
+        assert L.RNLHandler_SetRes(*[C.byref(x) for x in good]) == 0
+        bad = [T.vdt(a) for a in (y, u, v[:, :16], oy, ou, ov)]
+        assert L.RNLHandler_SetRes(*[C.byref(x) for x in bad]) == T.RNLErrorBadParameter
+        bad = [T.vdt(a) for a in (y, u, v, oy, ou, ov[:24])]
+        assert L.RNLHandler_SetRes(*[C.byref(x) for x in bad]) == T.RNLErrorBadParameter
+    finally:
+        L.RNLHandler_Deinit()

@@ -12,9 +12,9 @@ hin = [[torch.from_numpy(T.synth_frame(W, H, 8, 1234 + i)).pin_memory(), torch.f
 hout = [[torch.empty((2 * H, 2 * W), dtype=torch.uint8).pin_memory(), torch.empty((H, W), dtype=torch.uint8).pin_memory(),
          torch.empty((H, W), dtype=torch.uint8).pin_memory()] for _ in range(NB)]
 ref = None
-for name, env in (("default", {}), ("split_h2d=0", {"RAISR_CUDA_SPLIT_H2D": "0"}), ("zero_copy=0", {"RAISR_CUDA_ZERO_COPY": "0"}),
+for name, env in (("default", {}), ("split_h2d=0", {"RAISR_CUDA_SPLIT_H2D": "0"}), ("tail_in_place=0", {"RAISR_CUDA_TAIL_IN_PLACE": "0"}),
                   ("luma only default", {"_LUMA": "1"}), ("luma only split=0", {"_LUMA": "1", "RAISR_CUDA_SPLIT_H2D": "0"})):
-    for k in ("RAISR_CUDA_ZERO_COPY", "RAISR_CUDA_H2D_BANDS", "RAISR_CUDA_SPLIT_H2D"):
+    for k in ("RAISR_CUDA_TAIL_IN_PLACE", "RAISR_CUDA_SPLIT_H2D"):
         os.environ.pop(k, None)
     for k, v in env.items():
         if not k.startswith("_"):

@@ -46,8 +46,17 @@ RNLERRORTYPE RNLInit(std::string &modelPath, float ratio, unsigned int bitDepth,
 RNLERRORTYPE RNLSetRes(VideoDataType *inY, VideoDataType *inCr, VideoDataType *inCb, VideoDataType *outY,
                        VideoDataType *outCr, VideoDataType *outCb)
 {
-    (void)inCb; (void)outCb;
     if (!g_engine || !inY || !outY || !inCr || !outCr) return RNLErrorBadParameter;
+    // The reference builds ONE chroma resize spec from inCr/outCr and applies it to both planes (Raisr.cpp:1805-1812,1373-1388), i.e.
+    // it silently assumes Cb == Cr geometry -- true for every pixel format of vf_raisr.c:158-162.  Say so instead of assuming.
+    if (inCb && (inCb->width != inCr->width || inCb->height != inCr->height)) {
+        std::cout << "[RAISR ERROR] input Cb plane geometry differs from Cr" << std::endl;
+        return RNLErrorBadParameter;
+    }
+    if (outCb && (outCb->width != outCr->width || outCb->height != outCr->height)) {
+        std::cout << "[RAISR ERROR] output Cb plane geometry differs from Cr" << std::endl;
+        return RNLErrorBadParameter;
+    }
     return (RNLERRORTYPE)raisr_cuda_set_res(g_engine, inY->width, inY->height, outY->width, outY->height,
                                             inCr->width, inCr->height, outCr->width, outCr->height);
 }

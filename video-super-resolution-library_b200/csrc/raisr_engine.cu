@@ -124,10 +124,11 @@ struct raisr_cuda_engine {
     int blending = 2;               // BlendingMode of the frame being processed
     bool no_memops = false;         // RAISR_CUDA_NO_MEMOPS=1 (or CUDA_LAUNCH_BLOCKING=1): no in-kernel flag waits, everything in plain stream order
     bool split_h2d = true;          // pipelined kernel: input plane in two copies, the second one under the kernel; RAISR_CUDA_SPLIT_H2D=0 disables
-    int h2d_bands = 0;              // >1: input H2D split into row bands signalled to the already running kernel (measured slower than one copy: 960 vs 1023 frames/s); RAISR_CUDA_H2D_BANDS
-    int zero_copy = 4;              // bit 2: write the rows of the last round of tiles straight into a pinned output plane (no copy after the kernel), bit 0: read pinned input planes in place (measured slower: PCIe latency in stage A), bit 1: write pinned output planes in place (small PCIe writes from the SMs: 0.739 vs 0.724 ms per frame for the band-signalled copy-engine pipeline); RAISR_CUDA_ZERO_COPY overrides
-    int cluster = 1;                // RAISR_CUDA_CLUSTER=2: CTA pairs multicast the filter slices
-    bool use_pipe = true;           // persistent warp-specialised kernel (0.74 ms per 4K frame); RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (0.85 ms)
+    bool tail_in_place = true;      // rows of the last round of tiles go straight into a page-locked output plane (no copy after the kernel); RAISR_CUDA_TAIL_IN_PLACE=0 disables
+    bool band_pipeline = true;      // luma D2H in row bands under the kernel; RAISR_CUDA_NO_BAND_PIPELINE=1 disables
+    bool use_pipe = true;           // persistent warp-specialised kernel; RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (cross-check)
+    float gw[11][6] = {};           // folded Gaussian weights of this engine's bit depth (copied into every launch's parameters)
+    unsigned attr_set = 0;          // kernel instantiations whose dynamic shared-memory opt-in has been set on e->device (bit per instantiation)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
     // geometry
@@ -148,22 +149,26 @@ struct raisr_cuda_engine {
     cudaStream_t stream_d2h = nullptr;
     typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
     WaitValue32Fn wait_value32 = nullptr, write_value32 = nullptr;
-    unsigned *d_in_ready = nullptr;      // per input band: sequence number of the last frame whose rows have arrived
+    unsigned *d_in_ready = nullptr;      // sequence number of the last frame whose lower input rows (split H2D) have arrived
     unsigned frame_seq = 0;
+    unsigned *h_err = nullptr, *d_err = nullptr;   // page-locked, device-mapped word: an in-kernel flag wait timed out (checked after every frame)
     // RAISR_CUDA_TIMING=1: per-stage device times of the host-pointer call, printed when the engine is destroyed
     bool timing = false; cudaEvent_t tev[3] = {nullptr, nullptr, nullptr}; double t_h2d = 0, t_kern = 0; unsigned long long t_n = 0;
     unsigned *d_chroma_ready = nullptr;  // [0] sequence number of the last frame whose chroma planes have arrived (H2D on stream_uv), [1] CTAs done with them (running total)
     unsigned chroma_seq = 0, chroma_done_target = 0;
     unsigned band_target[kMaxBands] = {};  // running totals the D2H stream waits for, per output row band
     cudaStream_t stream_h2d = nullptr;
-    int last_grid_y = 0, last_tile_h = 0;   // geometry of the most recent pass launch
-    int last_grid_x = 0;                    // CTAs of the most recent launch that carried a chroma job
-    int last_banded_rows = 0;               // tile rows of the most recent launch that are signalled per band (the rest is written in place)
+    int last_chroma_ctas = 0;               // CTAs of the most recent launch that carried a chroma job (each bumps chroma_done once)
+    // row bands of the most recent launch with a band_done counter: computed ONCE (launch_pass_t) and used both for the kernel's
+    // band_tiles_y and for the host's wait targets / copy ranges
+    int n_bands = 0;
+    int band_row0[kMaxBands] = {}, band_row1[kMaxBands] = {};
+    unsigned band_tiles[kMaxBands] = {};
 };
 
 namespace {
 
-int fill_weights(unsigned bits)
+void fill_weights(raisr_cuda_engine *e, unsigned bits)
 {
     // the 21 distinct literals of gGaussian2DOriginal (Raisr_globals.h:213-224), G[i][j] = kG[min][max] after folding
     static const double kG[6][6] = {
@@ -175,41 +180,30 @@ int fill_weights(unsigned bits)
         {0, 0, 0, 0, 0, 0.0402265}};
     const float M = bits == 8 ? 255.0f : bits == 10 ? 1023.0f : 65535.0f;
     const float NF = 1.0f / (M * M * 2.0f * 2.0f);                       // NF_8 / NF_10 / NF_16, Raisr_globals.h:204-206
-    float w[11][6];
     for (int i = 0; i < 11; ++i) {
         const int ii = i < 5 ? i : 10 - i;
-        for (int m = 0; m < 6; ++m) w[i][m] = (float)((double)NF * kG[std::min(ii, m)][std::max(ii, m)]);
+        for (int m = 0; m < 6; ++m) e->gw[i][m] = (float)((double)NF * kG[std::min(ii, m)][std::max(ii, m)]);
     }
-    CUDA_OK(cudaMemcpyToSymbol(c_gw, w, sizeof(w)));
-    return 0;
 }
 
 template <typename PixT, int PT, int UPS>
 int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStream_t s)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    // The >48 KB dynamic shared-memory opt-in is a per-device function attribute: tracked per engine (an engine lives on one
+    // device), never in process-global state.
+    const unsigned bit = 1u << ((sizeof(PixT) == 2 ? 6 : 0) + (PT == 4 ? 3 : 0) + UPS);
+    if (!(e->attr_set & bit)) {
+        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         CUDA_OK(cudaFuncSetAttribute(raisr_pass_pipe_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES));
-        attr_done = true;
+        e->attr_set |= bit;
     }
     if (e->use_pipe) {
         // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
         const int ntiles = (int)(grid.x * grid.y);
-        if (q.chroma_n) e->last_grid_x = std::min(ntiles, e->num_sms);
+        if (q.chroma_n) e->last_chroma_ctas = std::min(ntiles, e->num_sms);
         raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NTP, PIPE_SMEM_BYTES, s>>>(q);
-    } else if (e->cluster == 2 && (grid.x % 2 == 0)) {
-        // pairs of horizontally neighbouring tiles form a thread-block cluster and share every filter-slice load
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
-        cudaLaunchAttribute at{};
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-        cfg.attrs = &at; cfg.numAttrs = 1;
-        CUDA_OK(cudaLaunchKernelEx(&cfg, raisr_pass_kernel<PixT, PT, UPS, 2>, q));
     } else {
-        raisr_pass_kernel<PixT, PT, UPS, 1><<<grid, NT, SMEM_BYTES, s>>>(q);
+        raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
     }
     CUDA_OK(cudaGetLastError());
     e->launches++;
@@ -228,7 +222,6 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
     while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && 2 * (ny + 1) <= rows) ++ny;
     q.tile_h = std::min(thmax, (((rows + ny - 1) / ny) + 1) & ~1);
     const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
-    e->last_grid_y = (int)grid.y; e->last_tile_h = q.tile_h;
     // tile rows of the last round of the persistent kernel (they finish together, at the very end): written in place into the
     // caller's pinned plane when there is one, so that no copy remains after the kernel; the bands cover the rows above
     int banded_rows = (int)grid.y;
@@ -238,8 +231,18 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
     } else {
         q.out_tail = nullptr;
     }
-    e->last_banded_rows = banded_rows;
-    if (q.band_done) q.band_tiles_y = std::max(1, (banded_rows + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands);
+    if (q.band_done) {
+        // the ONE place the band geometry is decided: tile rows per band for the kernel, rows and tile counts per band for the host
+        constexpr int kMax = raisr_cuda_engine::kMaxBands;
+        q.band_tiles_y = std::max(1, (banded_rows + kMax - 1) / kMax);
+        e->n_bands = 0;
+        for (int ty = 0; ty < banded_rows; ty += q.band_tiles_y) {
+            const int tiles_y = std::min(q.band_tiles_y, banded_rows - ty), b = e->n_bands++;
+            e->band_row0[b] = p.row0 + ty * q.tile_h;
+            e->band_row1[b] = std::min(p.row1, p.row0 + (ty + tiles_y) * q.tile_h);
+            e->band_tiles[b] = (unsigned)(tiles_y * gx);
+        }
+    }
     q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch | reinterpret_cast<uintptr_t>(q.out_tail) | (q.out_tail ? q.out_tail_pitch : 0)) % (4 * sizeof(PixT))) == 0;
     // 2x fast path: exact factor 2 in both axes and even band origin
     const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
@@ -297,6 +300,8 @@ void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
     p->blending = e->blending;
     p->lut_rsqrt14 = static_cast<const uint2 *>(e->d_lut[0]); p->lut_rcp14 = static_cast<const uint2 *>(e->d_lut[1]);
     p->lut_rsqrtps = static_cast<const uint16_t *>(e->d_lut[2]); p->lut_rcpps = static_cast<const uint16_t *>(e->d_lut[3]);
+    memcpy(p->gw, e->gw, sizeof(p->gw));
+    p->err_flag = e->d_err;
 }
 
 void set_upscale(const raisr_cuda_engine *e, PassParams *p)
@@ -331,7 +336,7 @@ void set_chroma(const raisr_cuda_engine *e, const ChromaJob *c, PassParams *p)
 
 // the luma launch plan; rows [row0,row1) of the final plane (row bands only for single-pass configurations)
 int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y, size_t out_step, int row0, int row1,
-             cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr, int in_band_rows = 0,
+             cudaStream_t s, unsigned *band_done = nullptr, const unsigned *in_ready = nullptr,
              const ChromaJob *chroma = nullptr, void *out_tail = nullptr, size_t out_tail_step = 0, int in_split_row = 0)
 {
     const bool two = e->cfg.passes == 2;
@@ -344,7 +349,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
         p.band_done = band_done; p.out_tail = out_tail; p.out_tail_pitch = out_tail_step;
-        p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_band_rows = in_band_rows; p.in_split_row = in_split_row;
+        p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_split_row = in_split_row;
         return launch_pass(e, p, s);
     }
     // Two passes on a row band: pass 1 is recomputed on the rows pass 2 can reach (+-7 output rows of pass 2, mapped back
@@ -370,7 +375,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
     p2.band_done = band_done; p2.out_tail = out_tail; p2.out_tail_pitch = out_tail_step;
-    p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_band_rows = in_band_rows; p1.in_split_row = in_split_row;
+    p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_split_row = in_split_row;
     set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
     int rc = launch_pass(e, p1, s);
     if (rc) return rc;
@@ -455,12 +460,11 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     }
     if (cudaGetDevice(&e->device) != cudaSuccess) return fail(RNLErrorInsufficientResources);
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
-    if (const char *z = std::getenv("RAISR_CUDA_ZERO_COPY")) e->zero_copy = std::atoi(z);
-    if (const char *c = std::getenv("RAISR_CUDA_CLUSTER")) e->cluster = std::atoi(c);
+    if (const char *z = std::getenv("RAISR_CUDA_TAIL_IN_PLACE")) e->tail_in_place = std::atoi(z) != 0;
+    if (const char *z = std::getenv("RAISR_CUDA_NO_BAND_PIPELINE")) e->band_pipeline = std::atoi(z) == 0;
     if (const char *sp = std::getenv("RAISR_CUDA_SPLIT_H2D")) e->split_h2d = std::atoi(sp) != 0;
     if (const char *nm = std::getenv("RAISR_CUDA_NO_MEMOPS")) e->no_memops = std::atoi(nm) != 0;
     if (const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING")) e->no_memops = e->no_memops || std::atoi(lb) != 0;
-    if (const char *b = std::getenv("RAISR_CUDA_H2D_BANDS")) e->h2d_bands = std::min(std::atoi(b), (int)raisr_cuda_engine::kMaxBands);
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
     if (std::getenv("RAISR_CUDA_TIMING")) { e->timing = true; for (auto &ev : e->tev) cudaEventCreate(&ev); }
     for (unsigned i = 0; i < passes; ++i) {
@@ -504,14 +508,18 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
                 cudaMemcpy(e->d_lut[i], src[i], bytes[i], cudaMemcpyHostToDevice) != cudaSuccess)
                 return fail(RNLErrorInsufficientResources);
     }
-    if (fill_weights(cfg->bit_depth)) return fail(RNLErrorInsufficientResources);
+    fill_weights(e, cfg->bit_depth);
+    // flags and counters shared with the running kernel: all start at zero (the D2H stream waits for RUNNING totals of band_done)
     if (cudaMalloc(&e->d_chroma_ready, 2 * sizeof(unsigned)) != cudaSuccess || cudaMemset(e->d_chroma_ready, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&e->d_in_ready, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
-        cudaMemset(e->d_in_ready, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+        cudaMalloc(&e->d_in_ready, sizeof(unsigned)) != cudaSuccess || cudaMemset(e->d_in_ready, 0, sizeof(unsigned)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&e->d_band_done, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking) != cudaSuccess)
+        cudaMemset(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void **>(&e->h_err), sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess)
         return fail(RNLErrorInsufficientResources);
+    *e->h_err = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->d_err), e->h_err, 0) != cudaSuccess) return fail(RNLErrorInsufficientResources);
     {
         // cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
         void *fn = nullptr;
@@ -604,7 +612,7 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
         for (unsigned i = 0; i < e->cfg.passes; ++i)
             if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
         const ChromaJob cj{{in_u, in_v}, {in_u_step, in_v_step}, {out_u, out_v}, {out_u_step, out_v_step}, nullptr, 0, nullptr};
-        return run_luma(e, in_y, in_y_step, out_y, out_y_step, 0, e->out_h, s, nullptr, nullptr, 0, &cj);
+        return run_luma(e, in_y, in_y_step, out_y, out_y_step, 0, e->out_h, s, nullptr, nullptr, &cj);
     }
     int rc = raisr_cuda_process_device_rows(e, in_y, in_y_step, out_y, out_y_step, blending, 0, e->out_h, stream);
     if (rc) return rc;
@@ -612,6 +620,194 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
     if (in_v && out_v) { rc = launch_resize(e, in_v, in_v_step, out_v, out_v_step, s); if (rc) return rc; }
     return RNLErrorNone;
 }
+
+}  // extern "C"
+
+namespace {
+
+// After a failed frame: nothing of it may leak into the next one.  The counters the copy streams wait on are running totals and
+// the flags are sequence numbers, so a frame that stopped half way (an enqueue error, a timed-out flag wait) leaves them out of
+// step with the host's shadow values: drain the device and start all of them from zero again.
+void resync_after_failure(raisr_cuda_engine *e)
+{
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    cudaMemset(e->d_band_done, 0, sizeof(unsigned) * raisr_cuda_engine::kMaxBands);
+    cudaMemset(e->d_chroma_ready, 0, 2 * sizeof(unsigned));
+    cudaMemset(e->d_in_ready, 0, sizeof(unsigned));
+    cudaDeviceSynchronize();
+    for (unsigned &t : e->band_target) t = 0;
+    e->chroma_seq = e->chroma_done_target = e->frame_seq = 0;
+    *e->h_err = 0;
+}
+
+int memop_failed(const char *what)
+{
+    std::cout << "[RAISR ERROR] " << what << " failed" << std::endl;
+    return (int)RNLErrorUndefined;
+}
+
+// Phase-sequential kernel (RAISR_CUDA_KERNEL=tile, the cross-check implementation): everything in plain stream order, chroma
+// on its own stream with one resize launch per plane.
+int process_host_tile(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u, size_t in_u_step, const void *in_v,
+                      size_t in_v_step, void *out_y, size_t out_y_step, void *out_u, size_t out_u_step, void *out_v, size_t out_v_step,
+                      bool chroma)
+{
+    const size_t bps = e->bps;
+    if (chroma) {
+        const void *src[2] = {in_u, in_v};
+        const size_t sstep[2] = {in_u_step, in_v_step};
+        void *dst[2] = {out_u, out_v};
+        const size_t dstep[2] = {out_u_step, out_v_step};
+        for (int i = 0; i < 2; ++i) {
+            CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
+                                      cudaMemcpyHostToDevice, e->stream_uv));
+            int rc = launch_resize(e, e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->stream_uv);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < 2; ++i)
+            CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
+                                      cudaMemcpyDeviceToHost, e->stream_uv));
+    }
+    CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
+    return RNLErrorNone;
+}
+
+// Pipelined kernel: ONE launch per pass carries the whole frame (the chroma planes ride along in the filter warps); the copies run
+// on three side streams under the kernel, ordered against it by flags (stream memory operations):
+//   luma in   : the first rows ahead of the launch, the rest on stream_h2d, flag in_ready  -> kernel (both reader groups wait)
+//   chroma in : behind the luma copies on stream_uv,              flag chroma_ready        -> kernel (filter warps wait)
+//   chroma out: kernel counts CTAs done with their share (chroma_done) -> stream_uv waits, copies the planes out
+//   luma out  : kernel counts finished tiles per row band (band_done)  -> stream_d2h waits per band, copies the band; the rows of
+//               the last round of tiles are written in place when the caller's plane is page-locked
+// Every copy the kernel waits for is enqueued BEFORE the launch.  Without stream memory operations (or RAISR_CUDA_NO_MEMOPS=1,
+// needed under tools that serialise the GPU) the same copies run in plain stream order around the kernel.
+int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u, size_t in_u_step, const void *in_v,
+                      size_t in_v_step, void *out_y, size_t out_y_step, void *out_u, size_t out_u_step, void *out_v, size_t out_v_step,
+                      bool chroma)
+{
+    const size_t bps = e->bps;
+    const bool memops = e->wait_value32 && e->write_value32 && !e->no_memops;
+    const void *csrc[2] = {in_u, in_v};
+    const size_t csstep[2] = {in_u_step, in_v_step};
+    void *cdst[2] = {out_u, out_v};
+    const size_t cdstep[2] = {out_u_step, out_v_step};
+
+    // ---- luma input: rows [0, split_row) ahead of the launch, the rest under the kernel ----------------------------------
+    int split_row = 0;
+    const unsigned *in_ready = nullptr;
+    if (memops && e->split_h2d && e->in_h >= 256) {
+        split_row = std::max(64, (e->in_h / 8 + 15) & ~15);
+        ++e->frame_seq;
+        in_ready = e->d_in_ready;
+    }
+    const int rows0 = split_row ? split_row : e->in_h;
+    if (e->timing) cudaEventRecord(e->tev[0], e->stream);
+    CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, rows0, cudaMemcpyHostToDevice, e->stream));
+    if (e->timing) cudaEventRecord(e->tev[1], e->stream);
+    if (split_row) {
+        CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));                      // part 2 behind part 1 (same copy engine anyway)
+        CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
+        CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
+                                  static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
+                                  cudaMemcpyHostToDevice, e->stream_h2d));
+        if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+        if (chroma) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));      // the chroma copies queue up behind the luma copies
+    } else if (chroma) {
+        CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
+    }
+
+    // ---- chroma input ------------------------------------------------------------------------------------------------
+    ChromaJob cj{};
+    if (chroma) {
+        for (int i = 0; i < 2; ++i) {
+            cj.in[i] = e->d_in[i + 1].ptr; cj.in_step[i] = e->d_in[i + 1].pitch;
+            cj.out[i] = e->d_out[i + 1].ptr; cj.out_step[i] = e->d_out[i + 1].pitch;
+        }
+        if (memops) {
+            cj.ready = e->d_chroma_ready; cj.seq = ++e->chroma_seq;          // H2D on the chroma stream, flagged to the running kernel
+            cj.done = e->d_chroma_ready + 1;                                 // D2H by the copy engine as soon as every CTA has written its share
+            CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
+            for (int i = 0; i < 2; ++i)
+                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
+                                          cudaMemcpyHostToDevice, e->stream_uv));
+            if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+        } else {
+            for (int i = 0; i < 2; ++i)
+                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
+                                          cudaMemcpyHostToDevice, e->stream));
+        }
+    }
+    for (unsigned i = 0; i < e->cfg.passes; ++i)
+        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
+
+    // ---- launch ------------------------------------------------------------------------------------------------------------
+    const bool band_d2h = memops && e->band_pipeline;
+    const void *tail_dev = nullptr;                                         // rows of the last round of tiles: in place when the plane is page-locked
+    const bool tail_direct = band_d2h && e->tail_in_place && mapped_host_pointer(out_y, &tail_dev);
+    int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream,
+                      band_d2h ? e->d_band_done : nullptr, in_ready, chroma ? &cj : nullptr,
+                      tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step, split_row);
+    if (rc) return rc;
+    if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+
+    // ---- chroma output -----------------------------------------------------------------------------------------------------
+    if (chroma) {
+        cudaStream_t cs = e->stream;
+        if (memops) {
+            cs = e->stream_uv;
+            e->chroma_done_target += (unsigned)e->last_chroma_ctas;          // running total: no reset, no race with the previous frame
+            if (e->wait_value32(cs, (unsigned long long)(uintptr_t)(e->d_chroma_ready + 1), e->chroma_done_target, 0 /* GEQ */) != 0)
+                return memop_failed("cuStreamWaitValue32");
+        }
+        for (int i = 0; i < 2; ++i)
+            CUDA_OK(cudaMemcpy2DAsync(cdst[i], cdstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
+                                      cudaMemcpyDeviceToHost, cs));
+    }
+
+    // ---- luma output -------------------------------------------------------------------------------------------------------
+    if (band_d2h) {
+        // The final pass counts finished tiles per row band (running totals, never reset); the D2H stream waits on each counter
+        // and copies that band while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
+        for (int b = 0; b < e->n_bands; ++b) {
+            e->band_target[b] += e->band_tiles[b];
+            if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), e->band_target[b], 0 /* GEQ */) != 0)
+                return memop_failed("cuStreamWaitValue32");
+            const int r0 = e->band_row0[b], r1 = e->band_row1[b];
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(out_y) + (size_t)r0 * out_y_step, out_y_step,
+                                      static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
+                                      e->out_w * bps, r1 - r0, cudaMemcpyDeviceToHost, e->stream_d2h));
+        }
+        if (!tail_direct && e->n_bands > 0 && e->band_row1[e->n_bands - 1] < e->out_h) {
+            // (not reached today: without an in-place tail every tile row belongs to a band)
+            const int r0 = e->band_row1[e->n_bands - 1];
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(out_y) + (size_t)r0 * out_y_step, out_y_step,
+                                      static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
+                                      e->out_w * bps, e->out_h - r0, cudaMemcpyDeviceToHost, e->stream));
+        }
+        CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
+    } else {
+        CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (split_row) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
+    if (chroma && memops) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
+    if (e->timing) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e->tev[0], e->tev[1]); cudaEventElapsedTime(&b, e->tev[1], e->tev[2]);
+        e->t_h2d += a; e->t_kern += b; e->t_n++;
+    }
+    return RNLErrorNone;
+}
+
+}  // namespace
+
+extern "C" {
 
 int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
                             size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
@@ -621,197 +817,15 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     if (check_blending(blending)) return RNLErrorBadParameter;
     e->blending = blending;
     CUDA_OK(cudaSetDevice(e->device));
-    const size_t bps = e->bps;
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
-    // stream memory operations (cuStreamWaitValue32 / WriteValue32) let copies run under the kernel, which then waits in-kernel for
-    // flags.  That needs copies and kernel to make progress concurrently: tools that serialise the GPU (compute-sanitizer,
-    // CUDA_LAUNCH_BLOCKING=1) must use the plain stream-ordered pipeline (RAISR_CUDA_NO_MEMOPS=1, implied by CUDA_LAUNCH_BLOCKING).
-    const bool memops = e->wait_value32 && e->write_value32 && !e->no_memops;
-    auto memop_failed = [](const char *what) { std::cout << "[RAISR ERROR] " << what << " failed" << std::endl; return (int)RNLErrorUndefined; };
-    // Pipelined kernel: the chroma planes are resized by the luma launch itself (its filter warps, early in the frame, while
-    // they would otherwise wait for the first bucket tiles); only the copies remain here.  Phase-sequential kernel: chroma on
-    // its own stream, both H2D copies and both resizes first, the D2H copies overlap the luma kernel.
-    const bool fused = chroma && e->use_pipe;
-    if (chroma && !fused) {
-        const void *src[2] = {in_u, in_v};
-        const size_t sstep[2] = {in_u_step, in_v_step};
-        for (int i = 0; i < 2; ++i) {
-            CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
-                                      cudaMemcpyHostToDevice, e->stream_uv));
-            int rc = launch_resize(e, e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->stream_uv);
-            if (rc) return rc;
-        }
-        void *dst[2] = {out_u, out_v};
-        const size_t dstep[2] = {out_u_step, out_v_step};
-        for (int i = 0; i < 2; ++i)
-            CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
-                                      cudaMemcpyDeviceToHost, e->stream_uv));
+    int rc = e->use_pipe ? process_host_pipe(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma)
+                         : process_host_tile(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma);
+    if (rc == RNLErrorNone && *reinterpret_cast<volatile unsigned *>(e->h_err) != 0) {
+        std::cout << "[RAISR ERROR] a copy the kernel was waiting for never arrived (flag wait timed out)" << std::endl;
+        rc = RNLErrorUndefined;
     }
-
-    // ---- luma input -------------------------------------------------------------------------------------------------------
-    // in place (pinned planes, RAISR_CUDA_ZERO_COPY bit 0; measured slower), in row bands on the H2D stream with the kernel
-    // launched first and waiting per tile for the rows it reads (RAISR_CUDA_H2D_BANDS), or one copy ahead of the kernel.
-    const void *k_in = e->d_in[0].ptr;
-    size_t k_in_step = e->d_in[0].pitch;
-    const bool in_direct = (e->zero_copy & 1) && mapped_host_pointer(in_y, &k_in);
-    if (in_direct) k_in_step = in_y_step;
-    const unsigned *in_ready = nullptr;
-    int in_band_rows = 0, split_row = 0;
-    const bool banded_h2d = !in_direct && e->h2d_bands > 1 && memops && !e->use_pipe;   // (the pipelined kernel: measured no gain, costs registers)
-    if (banded_h2d) {
-        ++e->frame_seq;
-        in_band_rows = (e->in_h + e->h2d_bands - 1) / e->h2d_bands;
-        in_ready = e->d_in_ready;
-    } else if (!in_direct) {
-        // Pipelined kernel: only the input rows the first tiles read are copied ahead of the launch; the rest follows on the H2D
-        // stream while the kernel works on those tiles, flagged to the chain warps (RAISR_CUDA_SPLIT_H2D=0: one copy).
-        if (e->use_pipe && memops && e->split_h2d && e->in_h >= 256) {
-            split_row = std::max(64, (e->in_h / 8 + 15) & ~15);
-            ++e->frame_seq;
-            in_ready = e->d_in_ready;
-        }
-        const int rows0 = split_row ? split_row : e->in_h;
-        if (e->timing) cudaEventRecord(e->tev[0], e->stream);
-        CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, rows0, cudaMemcpyHostToDevice, e->stream));
-        if (e->timing) cudaEventRecord(e->tev[1], e->stream);
-        if (split_row) {
-            CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));                  // part 2 behind part 1 (same copy engine anyway)
-            CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
-            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
-                                      static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
-                                      cudaMemcpyHostToDevice, e->stream_h2d));
-            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
-            if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));   // the chroma copies queue up behind the luma copies
-        } else if (fused) {
-            CUDA_OK(cudaEventRecord(e->ev_in, e->stream));                  // the chroma copies queue up behind the luma copy (same copy engine)
-        }
-    }
-
-    // ---- chroma job of the pipelined kernel -----------------------------------------------------------------------------
-    ChromaJob cj{};
-    bool chroma_early_d2h = false;
-    if (fused) {
-        for (int i = 0; i < 2; ++i) {
-            cj.in[i] = e->d_in[i + 1].ptr; cj.in_step[i] = e->d_in[i + 1].pitch;
-            cj.out[i] = e->d_out[i + 1].ptr; cj.out_step[i] = e->d_out[i + 1].pitch;
-        }
-        if (memops) {
-            cj.ready = e->d_chroma_ready; cj.seq = ++e->chroma_seq;          // H2D on the chroma stream, flagged to the running kernel
-            cj.done = e->d_chroma_ready + 1; chroma_early_d2h = true;        // D2H by the copy engine as soon as every CTA has written its share
-            if (!banded_h2d) {
-                // everything the kernel will wait for is enqueued BEFORE the launch (a blocking launch cannot starve it)
-                const void *src[2] = {in_u, in_v};
-                const size_t sstep[2] = {in_u_step, in_v_step};
-                if (!in_direct) CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
-                for (int i = 0; i < 2; ++i)
-                    CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
-                                              cudaMemcpyHostToDevice, e->stream_uv));
-                if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
-            }
-        } else {
-            const void *src[2] = {in_u, in_v};
-            const size_t sstep[2] = {in_u_step, in_v_step};
-            for (int i = 0; i < 2; ++i)
-                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
-                                          cudaMemcpyHostToDevice, e->stream));
-        }
-    }
-    // after the launch: banded luma H2D, chroma H2D behind it, chroma D2H once the kernel says the planes are written
-    auto after_launch = [&]() -> int {
-        if (banded_h2d) {
-            for (int b = 0; b * in_band_rows < e->in_h; ++b) {
-                const int r0 = b * in_band_rows, rows = std::min(in_band_rows, e->in_h - r0);
-                CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)r0 * e->d_in[0].pitch, e->d_in[0].pitch,
-                                          static_cast<const char *>(in_y) + (size_t)r0 * in_y_step, in_y_step, e->in_w * bps, rows,
-                                          cudaMemcpyHostToDevice, e->stream_h2d));
-                if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)(e->d_in_ready + b), e->frame_seq, 0) != 0)
-                    return memop_failed("cuStreamWriteValue32");
-            }
-            if (fused) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));
-        }
-        if (!fused) return 0;
-        void *dst[2] = {out_u, out_v};
-        const size_t dstep[2] = {out_u_step, out_v_step};
-        if (!memops) {                                                       // planes were copied in ahead of the kernel; out after it
-            for (int i = 0; i < 2; ++i)
-                CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
-                                          cudaMemcpyDeviceToHost, e->stream));
-            return 0;
-        }
-        if (banded_h2d) {                                                    // (phase-sequential kernel only: no fused chroma, kept for symmetry)
-            const void *src[2] = {in_u, in_v};
-            const size_t sstep[2] = {in_u_step, in_v_step};
-            CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
-            for (int i = 0; i < 2; ++i)
-                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, src[i], sstep[i], e->in_cw * bps, e->in_ch,
-                                          cudaMemcpyHostToDevice, e->stream_uv));
-            if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
-        }
-        e->chroma_done_target += (unsigned)e->last_grid_x;                   // running total: no reset, no race with the previous frame
-        if (e->wait_value32(e->stream_uv, (unsigned long long)(uintptr_t)(e->d_chroma_ready + 1), e->chroma_done_target, 0 /* GEQ */) != 0)
-            return memop_failed("cuStreamWaitValue32");
-        for (int i = 0; i < 2; ++i)
-            CUDA_OK(cudaMemcpy2DAsync(dst[i], dstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
-                                      cudaMemcpyDeviceToHost, e->stream_uv));
-        return 0;
-    };
-    (void)chroma_early_d2h;
-    const ChromaJob *cjp = fused ? &cj : nullptr;
-
-    for (unsigned i = 0; i < e->cfg.passes; ++i)
-        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
-
-    // ---- luma output ------------------------------------------------------------------------------------------------------
-    const void *out_dev = nullptr;
-    const bool out_direct = (e->zero_copy & 2) && mapped_host_pointer(out_y, &out_dev);
-    const bool band_d2h = !out_direct && memops && !std::getenv("RAISR_CUDA_NO_BAND_PIPELINE");
-    if (out_direct) {
-        // pinned caller plane written in place by the final pass (small PCIe writes from the SMs, spread over the kernel)
-        int rc = run_luma(e, k_in, k_in_step, const_cast<void *>(out_dev), out_y_step, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp, nullptr, 0, split_row);
-        if (rc) return rc;
-        if (e->timing) cudaEventRecord(e->tev[2], e->stream);
-        if ((rc = after_launch())) return rc;
-        CUDA_OK(cudaStreamSynchronize(e->stream));
-    } else if (band_d2h) {
-        // The final pass counts finished tiles per row band (running totals, never reset); the D2H stream waits on each counter
-        // and copies that band while the kernel is still working on the rows below (copies overlap compute inside ONE frame).
-        const void *tail_dev = nullptr;                                     // rows of the last round of tiles: in place when the plane is pinned
-        const bool tail_direct = (e->zero_copy & 4) && mapped_host_pointer(out_y, &tail_dev);
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, e->d_band_done, in_ready, in_band_rows, cjp,
-                          tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step, split_row);
-        if (rc) return rc;
-        if (e->timing) cudaEventRecord(e->tev[2], e->stream);
-        if ((rc = after_launch())) return rc;
-        const int gx = (e->out_w + TW - 1) / TW;
-        const int nrows_b = e->last_banded_rows;
-        const int bty = std::max(1, (nrows_b + raisr_cuda_engine::kMaxBands - 1) / raisr_cuda_engine::kMaxBands);
-        for (int b = 0, ty = 0; ty < nrows_b; ++b, ty += bty) {
-            const int tiles_y = std::min(bty, nrows_b - ty);
-            const int r0 = ty * e->last_tile_h, r1 = std::min(e->out_h, (ty + tiles_y) * e->last_tile_h);
-            e->band_target[b] += (unsigned)(tiles_y * gx);
-            if (e->wait_value32(e->stream_d2h, (unsigned long long)(uintptr_t)(e->d_band_done + b), e->band_target[b], 0 /* GEQ */) != 0)
-                return memop_failed("cuStreamWaitValue32");
-            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(out_y) + (size_t)r0 * out_y_step, out_y_step,
-                                      static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
-                                      e->out_w * bps, r1 - r0, cudaMemcpyDeviceToHost, e->stream_d2h));
-        }
-        CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
-        CUDA_OK(cudaStreamSynchronize(e->stream));
-    } else {
-        int rc = run_luma(e, k_in, k_in_step, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream, nullptr, in_ready, in_band_rows, cjp, nullptr, 0, split_row);
-        if (rc) return rc;
-        CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
-        if ((rc = after_launch())) return rc;
-        CUDA_OK(cudaStreamSynchronize(e->stream));
-    }
-    if (banded_h2d || split_row) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
-    if (chroma) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
-    if (e->timing && !in_direct && !banded_h2d) {
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e->tev[0], e->tev[1]); cudaEventElapsedTime(&b, e->tev[1], e->tev[2]);
-        e->t_h2d += a; e->t_kern += b; e->t_n++;
-    }
-    return RNLErrorNone;
+    if (rc != RNLErrorNone) resync_after_failure(e);
+    return rc;
 }
 
 int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count)
@@ -845,6 +859,7 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     cudaFree(e->d_in_ready);
     cudaFree(e->d_chroma_ready);
     cudaFree(e->d_band_done);
+    if (e->h_err) cudaFreeHost(e->h_err);
     if (e->stream_uv) cudaStreamDestroy(e->stream_uv);
     if (e->ev_uv) cudaEventDestroy(e->ev_uv);
     if (e->ev_in) cudaEventDestroy(e->ev_in);

@@ -44,10 +44,10 @@ struct PassParams {
     int nbuckets;            // 216
     int tile_h;              // output rows per CTA tile, <= TH_MAX (even)
     int vec_store;           // output base and pitch allow 4-pixel vector stores
-    const unsigned *in_ready; // optional: per input row band, the frame sequence number once its H2D copy has landed
+    const unsigned *in_ready; // optional (pipelined kernel, split H2D): set to in_seq once the lower part of the input plane has landed
     unsigned in_seq;         // sequence number of this frame
-    int in_band_rows;        // input rows per band
-    int in_split_row;        // pipelined kernel: input rows >= in_split_row are valid once *in_ready == in_seq (rows above: stream order)
+    int in_split_row;        // input rows >= in_split_row are valid once *in_ready == in_seq (rows above: stream order)
+    unsigned *err_flag;      // optional: set to 1 when an in-kernel flag wait times out (a copy the kernel waits for never landed)
     unsigned *band_done;     // optional: per row band, the number of finished tiles (host-side copy pipeline)
     int band_tiles_y;        // tile rows per band
     void *out_tail;          // optional: output rows >= tail_row0 go here instead (the caller's pinned plane, written in place:
@@ -76,10 +76,11 @@ struct PassParams {
     unsigned *chroma_done;          // optional: incremented once per CTA when its share of the chroma planes is written
     const uint2 *lut_rsqrt14, *lut_rcp14;      // x86 numerics: (c0,c1) runs of the 14-bit instructions, 128 entries each (may be null)
     const uint16_t *lut_rsqrtps, *lut_rcpps;   // x86 numerics: SSE approximation tables, 2048 entries each (may be null)
+    // Gaussian weights of this engine's bit depth, folded: gw[i][m] = w[i][m] = w[i][10-m], m = 0..5 (Raisr_globals.h:204-264).
+    // Part of the launch parameters (constant bank 0, read as uniform operands): per launch, hence per engine -- engines with
+    // different bit depths on one device cannot disturb each other.
+    alignas(8) float gw[11][6];
 };
-
-// Gaussian weights, folded: c_gw[i][m] = w[i][m] = w[i][10-m], m = 0..5   (Raisr_globals.h:208-264)
-__constant__ __align__(16) float c_gw[11][6];
 
 // ---- tile geometry -------------------------------------------------------------------------------
 constexpr int NT = 512;          // threads per CTA (one CTA per SM: the filter slice alone is 110 KB)
@@ -389,24 +390,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// bulk copy multicast to every CTA of the cluster named in cta_mask (same CTA-relative destination and mbarrier offsets)
-__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, unsigned bytes, void *bar, unsigned short cta_mask)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-                 : "memory");
-}
-__device__ __forceinline__ unsigned cluster_ctarank()
-{
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // The reference's 16 -> 1 lane tree (sumitup_ps_512, Raisr_AVX512.cpp:37-44) over the 8 lanes of a pixel, lane q holding
 // chains 2q (a0) and 2q+1 (a1):  t8[j] = acc[j] + acc[j+8];  t4[j] = t8[j] + t8[j+4];  t2[j] = t4[j] + t4[j+2];  t2[0] + t2[1].
@@ -527,10 +510,7 @@ __device__ __forceinline__ void stage_blend_store(const PassParams &p, const flo
 
 // UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),
 //      2 = any ratio through the per-axis tables (1.5x).   PT: pixel types (4 at 2x, else 1).
-// CL: CTAs per thread-block cluster (1 or 2).  With CL = 2 the two CTAs of a cluster (neighbouring tiles, neighbouring SMs)
-//     each fetch HALF of every filter slice and multicast it into both shared memories (TMA multicast), which halves the
-//     L2 -> SM traffic of the slice switches.
-template <typename PixT, int PT, int UPS, int CL>
+template <typename PixT, int PT, int UPS>
 __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -556,25 +536,6 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     if (tid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // (CL > 1: the first cluster barrier of stage D makes the initialised mbarrier visible to the peer before it signals it)
-
-    // The host may still be copying the lower part of the input plane (banded H2D on its own stream, each band followed
-    // by a stream write of the frame's sequence number): wait for the last input row this tile reads.
-    if (p.in_ready) {
-        if (tid == 0) {
-            const int ylast = min(H - 1, y0 + th + 6);
-            int in_last;
-            if (UPS == 0) in_last = ylast;
-            else if (UPS == 1) in_last = (ylast >> 1) + 1;
-            else in_last = (__ldg(p.ymap + ylast) >> 1) + 1;
-            const unsigned *flag = p.in_ready + min(in_last, p.in_h - 1) / p.in_band_rows;
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            } while (v != p.in_seq);
-        }
-        __syncthreads();
     }
 
     // ---- A: S tile ---------------------------------------------------------------------------------
@@ -650,7 +611,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
                     const float gx = sGX[(rl + i) * QW + q], gy = sGY[(rl + i) * QW + q];
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
-                        const float w = c_gw[i][m];
+                        const float w = p.gw[i][m];
                         const float px = fmul(gx, w), py = fmul(gy, w);
                         acc[m][0] = ffma(px, gx, acc[m][0]);
                         acc[m][1] = ffma(px, gy, acc[m][1]);
@@ -724,26 +685,12 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
         const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
         const float4 *sF4 = reinterpret_cast<const float4 *>(sF) + q;
         for (int t = 0; t < PT; ++t) {
-            if (CL > 1) {
-                // the peer CTA's multicast lands in THIS CTA's slice buffer too: both CTAs must be done with the buffer
-                // (chunk buffers / previous slice) before either one issues the next load
-                fence_proxy_async();
-                cluster_sync_all();
-            }
             if (tid == 0) {
                 fence_proxy_async();                              // generic-proxy accesses to the buffer are done (barrier above)
-                mbar_expect_tx(mbar, (unsigned)slice_bytes);      // the whole slice: own half + the peer's half
+                mbar_expect_tx(mbar, (unsigned)slice_bytes);
                 const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
-                if (CL == 1) {
-                    const int piece = slice_bytes / 4;            // 4 bulk copies (each a multiple of 16 bytes)
-                    for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mbar);
-                } else {
-                    const int half = slice_bytes / CL, piece = half / 2;
-                    const int base = (int)cluster_ctarank() * half;
-                    for (int i = 0; i < 2; ++i)
-                        bulk_g2s_multicast(reinterpret_cast<char *>(sF) + base + i * piece, src + base + i * piece, (unsigned)piece, mbar,
-                                           (unsigned short)((1u << CL) - 1));
-                }
+                const int piece = slice_bytes / 4;                // 4 bulk copies (each a multiple of 16 bytes)
+                for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mbar);
             }
             // pixels of type t inside the HR tile: frame parity (r-5)&1 == t>>1, (c-5)&1 == t&1   (Raisr.cpp:1068-1096)
             const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;

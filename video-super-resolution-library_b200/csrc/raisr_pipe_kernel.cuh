@@ -95,18 +95,38 @@ __device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
     return load_S<PixT>(p, Yc, Xc, UPS != 0);
 }
 
-// Split H2D: the lower part of the input plane (rows >= in_split_row) may still be on its way (own stream, flagged).  Called by
-// the chain warps before the ring fill of the first tile that reads such rows.  Not inlined, scalar arguments only (taking the
-// address of the kernel parameter block would move every access to it into local memory).
-__device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, int lt)
+// Bounded acquire-spin on a flag the host's copy streams write (cuStreamWriteValue32 behind a copy).  Every copy a kernel waits for
+// is enqueued before the launch, so the wait ends as soon as the copy engine gets there; should it never (a copy that failed), the
+// spin gives up after ~2 s of %globaltimer, raises *err (the host call then returns RNLErrorUndefined) and lets the kernel run on:
+// wrong rows in a frame that is reported as failed, never a hung device.
+__device__ __forceinline__ void spin_wait_flag(const unsigned *flag, unsigned seq, unsigned *err)
 {
-    if (lt == 0) {
+    unsigned long long t0 = 0;
+    for (unsigned n = 1;; ++n) {
         unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        } while (v != seq);
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == seq) return;
+        if ((n & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            volatile unsigned *verr = err;                                   // page-locked host word (plain stores: no PCIe atomics needed)
+            const bool failed = verr && *verr != 0;                          // another CTA has already given up
+            if (failed || t - t0 > 2000000000ull) {
+                if (verr) { *verr = 1u; __threadfence_system(); }
+                return;
+            }
+        }
     }
-    group_sync(BAR_CHAIN, NBT);
+}
+
+// Split H2D: the lower part of the input plane (rows >= in_split_row) may still be on its way (own stream, flagged).  Called by
+// a warp group (its leader spins, the group's named barrier publishes the result) before the first access to such rows.  Not inlined, scalar arguments only (taking the
+// address of the kernel parameter block would move every access to it into local memory).
+__device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader, int bar, int count)
+{
+    if (leader) spin_wait_flag(flag, seq, err);
+    group_sync(bar, count);
 }
 
 // Chroma planes: plain cheap upscale (Raisr.cpp:1373-1388) of this CTA's share of the planes, slice sl of nslices, by the filter
@@ -117,7 +137,7 @@ struct ChromaParams {
     int c_in_w, c_in_h, c_W, c_H;
     const int *c_xmap, *c_xw, *c_ymap, *c_yw;
     int c_denx, c_deny;
-    const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done;
+    const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done; unsigned *err_flag;
 };
 template <typename PixT>
 __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int nslices, int ct)
@@ -130,12 +150,7 @@ __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int 
     p.c_xmap = cp.c_xmap; p.c_xw = cp.c_xw; p.c_ymap = cp.c_ymap; p.c_yw = cp.c_yw; p.c_denx = cp.c_denx; p.c_deny = cp.c_deny;
     p.chroma_ready = cp.chroma_ready; p.chroma_seq = cp.chroma_seq; p.chroma_done = cp.chroma_done;
     if (sl == 0 && p.chroma_ready) {                                 // the planes' H2D copies run on their own stream
-        if (ct == 0) {
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.chroma_ready) : "memory");
-            } while (v != p.chroma_seq);
-        }
+        if (ct == 0) spin_wait_flag(p.chroma_ready, p.chroma_seq, cp.err_flag);
         group_sync(BAR_CONS, NCT);
     }
     if (p.c_W == 2 * p.c_in_w && p.c_H == 2 * p.c_in_h && p.c_denx == 4 && p.c_deny == 4) {
@@ -316,7 +331,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
                     const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
 #pragma unroll
                     for (int mm = 0; mm < 3; ++mm) {
-                        const f32x2 w2 = pack2(c_gw[i][2 * mm], c_gw[i][2 * mm + 1]);
+                        const f32x2 w2 = pack2(p.gw[i][2 * mm], p.gw[i][2 * mm + 1]);
                         const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
                         acc[mm][0] = fma2(px, gx2, acc[mm][0]);
                         acc[mm][1] = fma2(px, gy2, acc[mm][1]);
@@ -369,13 +384,13 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             };
             const int nchunks = hh / RBP;
             if (chain_warp) {
-                // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Only the chain warps
-                // look: the filter warps work on a tile the chain warps have already seen, and tiles come in row order.
+                // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Both reader groups
+                // look for themselves (the filter warps' stage A below): neither is ordered behind the other's wait.
                 if (p.in_ready && !input_complete) {
                     const int ylast = min(H - 1, y0 + th + 6);
                     const int in_last = (UPS == 0) ? ylast : (UPS == 1) ? (ylast >> 1) + 1 : (__ldg(p.ymap + ylast) >> 1) + 1;
                     if (in_last >= p.in_split_row) {
-                        wait_split_input(p.in_ready, p.in_seq, lt);
+                        wait_split_input(p.in_ready, p.in_seq, p.err_flag, lt == 0, BAR_CHAIN, NBT);
                         input_complete = true;
                     }
                 }
@@ -443,7 +458,6 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             }
         const float flo = (float)p.lo, fhi = (float)p.hi;
         const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
-        const float4 *sF4 = reinterpret_cast<const float4 *>(sF) + q;
         // per-lane constant parts of the fast block's shared addresses (bytes): pixel group g, lane q of the group
         unsigned poff[8][2];                                              // patch tap (m, e) of the group's pixel in block column 0
 #pragma unroll
@@ -467,18 +481,32 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             for (int i = 0; i < 2; ++i) { cp.in[i] = p.chroma[i].in; cp.in_pitch[i] = p.chroma[i].in_pitch; cp.out[i] = p.chroma[i].out; cp.out_pitch[i] = p.chroma[i].out_pitch; }
             cp.c_in_w = p.c_in_w; cp.c_in_h = p.c_in_h; cp.c_W = p.c_W; cp.c_H = p.c_H;
             cp.c_xmap = p.c_xmap; cp.c_xw = p.c_xw; cp.c_ymap = p.c_ymap; cp.c_yw = p.c_yw; cp.c_denx = p.c_denx; cp.c_deny = p.c_deny;
-            cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done;
+            cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done; cp.err_flag = p.err_flag;
             chroma_slice_fn<PixT>(cp, sl, nslices, ct);
         };
         unsigned nload = 0;
         int resident_type = -1;                                           // pixel type whose filter slice is in shared memory
         int iter = 0;
+        bool input_complete = false;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
             const int buf = iter & 1;
             const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
             const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
             const int ty = tile / gx, tx = tile - ty * gx;
             const int x0 = tx * TW, y0 = p.row0 + ty * th;
+            // split H2D (see the chain warps): stage A reads the same input rows as the chain warps' ring of this tile, and nothing
+            // else orders it behind their flag wait.  For the first tile that reaches into the flagged rows the filter warps
+            // therefore take this tile's FULL barrier BEFORE stage A instead of after it: the buckets of the tile exist only once
+            // the chain warps have seen the flag (leader's ld.acquire -> BAR_CHAIN -> BAR_PROD -> BAR_FULL, causality is cumulative).
+            bool full_taken = false;
+            if (p.in_ready && !input_complete) {
+                const int ylast = min(H - 1, y0 + th + 6);
+                const int in_last = (UPS == 0) ? ylast : (UPS == 1) ? (ylast >> 1) + 1 : (__ldg(p.ymap + ylast) >> 1) + 1;
+                if (in_last >= p.in_split_row) {
+                    group_sync(BAR_FULL + buf, NBT + NCT);
+                    full_taken = input_complete = true;
+                }
+            }
 
             // ---- A: S tile (the HR tile is free until the HR := S copy below: low-res staging for the 2x path; the slice buffer
             // keeps the previous tile's last filter slice) ----
@@ -521,7 +549,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
             }
             if (p.chroma_n > 0 && iter >= 2 && slices_done < nslices) chroma_slice(slices_done++);
             group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
-            group_sync(BAR_FULL + buf, NBT + NCT);                            // buckets of this tile are ready
+            if (!full_taken) group_sync(BAR_FULL + buf, NBT + NCT);           // buckets of this tile are ready
 
             // ---- D: 121-tap filter, one pixel type at a time ----
             const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
