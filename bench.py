@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- frames/s of the RAISR luma+chroma hot path on B200 (BASELINE.json configs[1]):
-1080p -> 4K yuv420p, filters_2x/filters_lowres, passes=1, bits=8.
+"""bench.py -- frames/s of the RAISR luma+chroma hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one batch of FRAMES_PER_STEP frames through the whole per-frame path (luma pass kernel + two chroma
-resizes).  `value` = frames/s with the planes already resident in HBM (device entry point of the C ABI, CUDA events
-on the launching stream); `e2e` = frames/s through the blocking host-pointer call RNLHandler_Process binds
-(pinned host planes, H2D and D2H inside the timed region).  Multi-GPU = frame-parallel shards (each rank its own
-frames, no data-path collective): weak scaling.  Prints ONE JSON line on rank 0.
+Headline workload = BASELINE.json configs[1]: 1080p -> 4K yuv420p, filters_2x/filters_lowres, passes=1, bits=8.
+One step = FRAMES_PER_STEP frames through the whole per-frame path (one fused launch: luma pass + both chroma resizes).
+  value         frames/s with the planes resident in HBM (device entry of the C ABI, CUDA events on the launching stream)
+  e2e           frames/s through RNLHandler_Process (the plugin symbol vf_raisr.c binds) with page-locked HOST planes,
+                H2D and D2H inside the timed region;  e2e_pageable: the same call with ordinary (pageable) planes
+  configs       sub-records for the other BASELINE configurations (N=1 only): device ms/frame, e2e frames/s, roofline
+  rowband       N>1 only: BASELINE configs[3] (4K->8K, 10-bit, 2 passes mode 2) as ONE frame split into row bands across
+                the ranks (strong scaling), bands gathered over NCCL, assembled frame asserted == the single-GPU frame
+Multi-GPU headline = frame-parallel shards (each rank its own frames, no data-path collective): weak scaling.
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
@@ -27,13 +31,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import raisr_testlib as T  # noqa: E402  (synthetic frames + the reference/oracle bindings for the CPU legs)
 
-IN_W, IN_H, OUT_W, OUT_H = 1920, 1080, 3840, 2160
-FOLDER = "filters_2x/filters_lowres"
 FRAMES_PER_STEP = 16
-NBUF = 12                      # distinct in/out frame sets rotated through: 12 x 15.55 MB = 187 MB > 126 MB L2
-BYTES_Y = IN_W * IN_H + OUT_W * OUT_H                       # algorithmic bytes of the luma kernel per launch
-BYTES_FRAME = BYTES_Y + 2 * (IN_W // 2 * IN_H // 2 + OUT_W // 2 * OUT_H // 2)
-WORKLOAD = "1080p->4K yuv420p, filters_2x/filters_lowres, passes=1, bits=8"
+L2_BYTES = 126e6
+
+# BASELINE.json configs (index -> workload).  yuv420p unless y_only.
+CONFIGS = {
+    "configs[0]": dict(folder="filters_2x/filters_lowres", ratio=2.0, bits=8, passes=1, mode=1, size=(960, 540), y_only=True,
+                       workload="540p->1080p Y-only, filters_2x/filters_lowres, passes=1, bits=8"),
+    "configs[1]": dict(folder="filters_2x/filters_lowres", ratio=2.0, bits=8, passes=1, mode=1, size=(1920, 1080), y_only=False,
+                       workload="1080p->4K yuv420p, filters_2x/filters_lowres, passes=1, bits=8"),
+    "configs[2]": dict(folder="filters_2x/filters_highres", ratio=2.0, bits=8, passes=2, mode=1, size=(1920, 1080), y_only=False,
+                       workload="1080p->4K yuv420p, filters_2x/filters_highres, passes=2 mode=1, bits=8"),
+    "configs[3]": dict(folder="filters_2x/filters_denoise", ratio=2.0, bits=10, passes=2, mode=2, size=(3840, 2160), y_only=False,
+                       workload="4K->8K yuv420p, filters_2x/filters_denoise, passes=2 mode=2, bits=10 (fp32 arithmetic)"),
+    # configs[4] as written (filters_1.5x/filters_highres, passes=2) cannot run anywhere: the folder ships no pass-2 tables
+    # (RNLInit fails in the reference too); its geometry is measured with both 1.5x folders instead
+    "configs[4]/highres-p1": dict(folder="filters_1.5x/filters_highres", ratio=1.5, bits=8, passes=1, mode=1, size=(1280, 720),
+                                  y_only=False, workload="720p->1080p 1.5x yuv420p, filters_1.5x/filters_highres, passes=1, bits=8"),
+    "configs[4]/denoise-p2": dict(folder="filters_1.5x/filters_denoise", ratio=1.5, bits=8, passes=2, mode=2, size=(1280, 720),
+                                  y_only=False, workload="720p->1080p 1.5x yuv420p, filters_1.5x/filters_denoise, passes=2 mode=2, bits=8"),
+}
+HEAD = CONFIGS["configs[1]"]
+WORKLOAD = HEAD["workload"]
+METRIC = "frames/sec 1080p->4K 2x RAISR (yuv420p frame: Y pass + chroma resize)"
+
+
+def geometry(c):
+    w, h = c["size"]
+    oW, oH = int(w * c["ratio"]), int(h * c["ratio"])
+    bps = 1 if c["bits"] == 8 else 2
+    by = (w * h + oW * oH) * bps                                         # algorithmic bytes of the luma path per frame
+    bc = 0 if c["y_only"] else 2 * ((w // 2) * (h // 2) + (oW // 2) * (oH // 2)) * bps
+    return w, h, oW, oH, bps, by, bc
 
 
 def load_binding():
@@ -46,9 +75,9 @@ def load_binding():
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -91,99 +120,173 @@ class ClockSampler:
         return out
 
 
+class quiet_stdout:
+    """The libraries print banners on fd 1; the bench prints exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.devnull = os.open(os.devnull, os.O_WRONLY)
+        self.saved = os.dup(1)
+        os.dup2(self.devnull, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.devnull)
+        os.close(self.saved)
+
+
+def synth_planes(c, seed):
+    w, h = c["size"]
+    bits = c["bits"]
+    y = T.synth_frame(w, h, bits, seed)
+    if c["y_only"]:
+        return [y]
+    return [y, T.synth_chroma(w // 2, h // 2, bits, seed + 1), T.synth_chroma(w // 2, h // 2, bits, seed + 2)]
+
+
+def out_shapes(c):
+    w, h, oW, oH, *_ = geometry(c)
+    return [(oH, oW)] if c["y_only"] else [(oH, oW), (oH // 2, oW // 2), (oH // 2, oW // 2)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs: the reference's own implementation (oracle/_ref = untouched sources + IPP stand-in) on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def ref_handler_fps(c, threads, asm, frames, warm=1):
+    """frames/s of RNLHandler_Process of the compiled reference in a FRESH process (its configuration lives in process
+    globals that RNLInit does not reset, Raisr_globals.h:140-203)."""
+    code = (
+        "import sys, time, ctypes as C, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import raisr_testlib as T\n"
+        "import bench as Bn\n"
+        "c = Bn.CONFIGS[%r]\n"
+        "L = T.handler_lib(T.ref_lib_path())\n"
+        "ins = Bn.synth_planes(c, 1234)\n"
+        "if c['y_only']:\n"
+        "    w, h = c['size']; ins += [T.synth_chroma(w // 2, h // 2, c['bits'], 1), T.synth_chroma(w // 2, h // 2, c['bits'], 2)]\n"
+        "shp = Bn.out_shapes(dict(c, y_only=False))\n"
+        "outs = [np.zeros(s, ins[0].dtype) for s in shp]\n"
+        "refs = [C.byref(x) for x in [T.vdt(a) for a in ins + outs]]\n"
+        "with Bn.quiet_stdout():\n"
+        "    assert L.RNLHandler_Init(T.filter_folder(c['folder']).encode(), c['ratio'], c['bits'], T.VideoRange, %d, %d, c['passes'], c['mode']) == 0\n"
+        "    assert L.RNLHandler_SetRes(*refs) == 0\n"
+        "    for _ in range(%d): L.RNLHandler_Process(*refs, T.CountOfBitsChanged)\n"
+        "    t0 = time.perf_counter()\n"
+        "    for _ in range(%d): L.RNLHandler_Process(*refs, T.CountOfBitsChanged)\n"
+        "    dt = time.perf_counter() - t0\n"
+        "    L.RNLHandler_Deinit()\n"
+        "print(%d / dt)\n"
+    ) % (os.path.join(ROOT, "tests"), c, threads, asm, warm, frames, frames)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.check_output([sys.executable, "-c", code], env=env, cwd=ROOT)
+    return float(out.decode().strip().splitlines()[-1])
+
+
 def reference_arm(args, rank):
-    """The reference's own CPU implementation of the path (oracle/_ref = untouched sources + IPP stand-in),
-    all host threads, bounded sample per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path, all host threads, on the headline workload,
+    FRAMES_PER_STEP frames per step like the B200 arm."""
     if rank != 0:
         return
-    L = T.handler_lib(T.ref_lib_path())
+    c = HEAD
     threads = os.cpu_count() or 1
-    frames = 2                                                 # frames per step: bounded sample of the workload
-    folder = T.filter_folder(FOLDER)
-    y = T.synth_frame(IN_W, IN_H, 8, 1234)
-    u, v = T.synth_chroma(IN_W // 2, IN_H // 2, 8, 1), T.synth_chroma(IN_W // 2, IN_H // 2, 8, 2)
-    oy = np.zeros((OUT_H, OUT_W), np.uint8)
-    ou = np.zeros((OUT_H // 2, OUT_W // 2), np.uint8)
-    ov = np.zeros_like(ou)
-    vs = [T.vdt(a) for a in (y, u, v, oy, ou, ov)]
-    refs = [ctypes.byref(x) for x in vs]
-    sys.stdout.flush()
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)                                        # the library prints a banner on stdout
-    try:
-        assert L.RNLHandler_Init(folder.encode(), 2.0, 8, T.VideoRange, threads, T.AVX512, 1, 1) == 0
+    L = T.handler_lib(T.ref_lib_path())
+    ins = synth_planes(c, 1234)
+    outs = [np.zeros(s, np.uint8) for s in out_shapes(c)]
+    refs = [ctypes.byref(x) for x in [T.vdt(a) for a in ins + outs]]
+    with quiet_stdout():
+        assert L.RNLHandler_Init(T.filter_folder(c["folder"]).encode(), 2.0, 8, T.VideoRange, threads, T.AVX512, 1, 1) == 0
         assert L.RNLHandler_SetRes(*refs) == 0
         for _ in range(args.warmup):
-            for _ in range(frames):
+            for _ in range(FRAMES_PER_STEP):
                 L.RNLHandler_Process(*refs, T.CountOfBitsChanged)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            for _ in range(frames):
+            for _ in range(FRAMES_PER_STEP):
                 L.RNLHandler_Process(*refs, T.CountOfBitsChanged)
         dt = time.perf_counter() - t0
         L.RNLHandler_Deinit()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved, 1)
-        os.close(devnull)
-    fps = args.steps * frames / dt
+    fps = args.steps * FRAMES_PER_STEP / dt
     line = {
-        "impl": "reference", "metric": "frames/sec 1080p->4K 2x RAISR (yuv420p frame: Y pass + chroma resize)",
-        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": frames},
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference",
-                         "sample": "%d frames per step of the same 1080p->4K workload; untouched reference sources, "
-                                   "AVX512 fp32 path, threadcount=%d, IPP replaced by oracle/ipp_standin" % (frames, threads)},
+                         "sample": "%d frames per step of the same 1080p->4K yuv420p workload; untouched reference sources, AVX512 fp32 "
+                                   "path, threadcount=%d, IPP replaced by oracle/ipp_standin" % (FRAMES_PER_STEP, threads)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def cpu_baseline_leg():
-    """oracle/_ref timed on this host's cores: bounded sample (about 10-30 s of CPU work)."""
+    """oracle/_ref timed on this host's cores: bounded sample (10-30 s of CPU work in total)."""
     if not T.have_ref():
-        # fall back to the C restatement (single thread)
-        folder = T.filter_folder(FOLDER)
+        folder = T.filter_folder(HEAD["folder"])
         m = T.OracleModel(folder, 8)
-        y = T.synth_frame(IN_W // 2, IN_H // 2, 8, 1234)
+        y = T.synth_frame(960, 540, 8, 1234)
         t0 = time.perf_counter()
-        T.oracle_process_y(y, IN_W, IN_H, m)
+        T.oracle_process_y(y, 1920, 1080, m)
         dt = time.perf_counter() - t0
         return {"value": 0.25 / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                 "sample": "one 540p->1080p luma frame (1/4 of the workload's pixels) through oracle/raisr_oracle.c, scaled by 1/4"}
-    L = T.handler_lib(T.ref_lib_path())
     threads = os.cpu_count() or 1
-    folder = T.filter_folder(FOLDER)
-    y = T.synth_frame(IN_W, IN_H, 8, 1234)
-    u, v = T.synth_chroma(IN_W // 2, IN_H // 2, 8, 1), T.synth_chroma(IN_W // 2, IN_H // 2, 8, 2)
-    oy = np.zeros((OUT_H, OUT_W), np.uint8)
-    ou = np.zeros((OUT_H // 2, OUT_W // 2), np.uint8)
-    ov = np.zeros_like(ou)
-    refs = [ctypes.byref(x) for x in [T.vdt(a) for a in (y, u, v, oy, ou, ov)]]
-    sys.stdout.flush()
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)
+    fps_n = ref_handler_fps("configs[1]", threads, T.AVX512, 24)
+    out = {"value": fps_n, "unit": "frames/s", "cores": threads, "kind": "reference",
+           "sample": "24 frames of the same 1080p->4K yuv420p workload after 1 warm-up; untouched reference sources (AVX512 fp32 path, "
+                     "threadcount=%d), IPP replaced by oracle/ipp_standin" % threads}
+    # BASELINE.md section 3: threadcount=1 beside nproc, the FP16 path for context, the stand-in resize on its own
     try:
-        assert L.RNLHandler_Init(folder.encode(), 2.0, 8, T.VideoRange, threads, T.AVX512, 1, 1) == 0
-        assert L.RNLHandler_SetRes(*refs) == 0
-        L.RNLHandler_Process(*refs, T.CountOfBitsChanged)
-        n, t0 = 0, time.perf_counter()
-        while n < 12 or (time.perf_counter() - t0 < 2.0 and n < 64):
-            L.RNLHandler_Process(*refs, T.CountOfBitsChanged)
-            n += 1
-        dt = time.perf_counter() - t0
-        L.RNLHandler_Deinit()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved, 1)
-        os.close(devnull)
-    return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "reference",
-            "sample": "%d frames of the same 1080p->4K yuv420p workload after 1 warm-up; untouched reference sources "
-                      "(AVX512 fp32 path, threadcount=%d), IPP replaced by oracle/ipp_standin" % (n, threads)}
+        extra = {"avx512_threads1_fps": ref_handler_fps("configs[1]", 1, T.AVX512, 3)}
+        if "avx512_fp16" in open("/proc/cpuinfo").read():
+            extra["avx512fp16_threads%d_fps" % threads] = ref_handler_fps("configs[1]", threads, T.AVX512_FP16, 24)
+        y = T.synth_frame(1920, 1080, 8, 1234)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            T.oracle_resize(y, 3840, 2160)
+        extra["standin_resize_ms_per_4k_luma_1thread"] = 1e3 * (time.perf_counter() - t0) / 3
+        extra["note"] = ("the stand-in resize is scalar C; real IPP would make the reference somewhat faster than measured here "
+                         "(per frame it runs once per luma band and once per chroma plane)")
+        out["context"] = extra
+    except Exception as ex:          # context only: never fail the bench for it
+        out["context"] = {"error": repr(ex)}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# NUMA placement of a rank: CPU affinity + preferred memory node of its GPU, BEFORE any page-locked allocation
+# ----------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    info = {"node": None, "cpus": None, "mempolicy": None}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpus"] = len(use)
+        # set_mempolicy(MPOL_PREFERRED, node): page-locked planes allocated from now on live next to the GPU's root complex
+        mask = ctypes.c_ulong(1 << node)
+        rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+        info["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+    except Exception as ex:
+        info["error"] = repr(ex)
+    return info
 
 
 def main():
@@ -192,6 +295,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -206,53 +310,18 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the RAISR engine has no CPU path")
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["RAISR_CUDA_DEVICE"] = str(local)                 # the RNLHandler_* engine of this process lives on this rank's GPU
 
     B = load_binding()
-    folder = T.filter_folder(FOLDER)
-    eng = B.Engine(folder, 2.0, 8, T.VideoRange, 1, 1, device=local, numerics=B.NUMERICS_AUTO)
-    eng.set_res(IN_W, IN_H, OUT_W, OUT_H, IN_W // 2, IN_H // 2, OUT_W // 2, OUT_H // 2)
-
-    # ---- synthetic frames: NBUF distinct sets, pinned on the host and resident on the device -----------------
-    dev = torch.device("cuda", local)
-    h_in, d_in, h_out, d_out = [], [], [], []
-    for i in range(NBUF):
-        seed = 1234 + 97 * rank + i
-        planes = [T.synth_frame(IN_W, IN_H, 8, seed), T.synth_chroma(IN_W // 2, IN_H // 2, 8, seed + 1),
-                  T.synth_chroma(IN_W // 2, IN_H // 2, 8, seed + 2)]
-        hp = [torch.from_numpy(p).pin_memory() for p in planes]
-        h_in.append(hp)
-        d_in.append([p.to(dev) for p in hp])
-        ho = [torch.empty((OUT_H, OUT_W), dtype=torch.uint8).pin_memory(),
-              torch.empty((OUT_H // 2, OUT_W // 2), dtype=torch.uint8).pin_memory(),
-              torch.empty((OUT_H // 2, OUT_W // 2), dtype=torch.uint8).pin_memory()]
-        h_out.append(ho)
-        d_out.append([torch.empty_like(o, device=dev) for o in ho])
-    torch.cuda.synchronize()
+    H = T.handler_lib(T.product_lib_path())                      # the plugin symbols (RNLHandler_*) of libraisr.so
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-
-    def dev_frame(i):
-        a, o = d_in[i % NBUF], d_out[i % NBUF]
-        rc = eng.process_device(a[0].data_ptr(), a[0].stride(0), o[0].data_ptr(), o[0].stride(0),
-                                a[1].data_ptr(), a[1].stride(0), a[2].data_ptr(), a[2].stride(0),
-                                o[1].data_ptr(), o[1].stride(0), o[2].data_ptr(), o[2].stride(0), 2, sptr)
-        assert rc == 0
-
-    def luma_only(i):
-        a, o = d_in[i % NBUF], d_out[i % NBUF]
-        rc = eng.process_device_rows(a[0].data_ptr(), a[0].stride(0), o[0].data_ptr(), o[0].stride(0), 0, OUT_H, 2, sptr)
-        assert rc == 0
-
-    def host_frame(i):
-        a, o = h_in[i % NBUF], h_out[i % NBUF]
-        rc = eng.L.raisr_cuda_process_host(eng.h, a[0].data_ptr(), a[0].stride(0), a[1].data_ptr(), a[1].stride(0),
-                                           a[2].data_ptr(), a[2].stride(0), o[0].data_ptr(), o[0].stride(0),
-                                           o[1].data_ptr(), o[1].stride(0), o[2].data_ptr(), o[2].stride(0), 2)
-        assert rc == 0
 
     def barrier():
         if world > 1:
@@ -266,88 +335,257 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput ("value") --------------------------------------------------------------
-    n = 0
-    for _ in range(args.warmup):
-        for _ in range(FRAMES_PER_STEP):
-            dev_frame(n); n += 1
+    def tdt(bits):
+        return torch.uint8 if bits == 8 else torch.int16
+
+    def to_torch(a):
+        return torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+
+    class Workload:
+        """Engine + rotating frame sets (device-resident and host) of one configuration."""
+
+        def __init__(self, c, nbuf=None, seed0=1234, pinned=True):
+            self.c = c
+            w, h, oW, oH, bps, by, bc = geometry(c)
+            self.bytes_y, self.bytes_frame, self.bps = by, by + bc, bps
+            self.nbuf = nbuf or int(min(64, max(2, -(-1.1 * L2_BYTES // (by + bc)))))
+            self.eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
+                                numerics=B.NUMERICS_AUTO)
+            if c["y_only"]:
+                self.eng.set_res(w, h, oW, oH)
+            else:
+                self.eng.set_res(w, h, oW, oH, w // 2, h // 2, oW // 2, oH // 2)
+            base = [synth_planes(c, seed0 + 97 * rank + i) for i in range(min(self.nbuf, 3))]
+            self.h_in, self.d_in, self.h_out, self.d_out = [], [], [], []
+            for i in range(self.nbuf):
+                src = base[i % len(base)]
+                if i >= len(base):                               # further sets: the base frames rolled (distinct addresses and content)
+                    src = [np.roll(p, 17 * i, axis=1) for p in src]
+                hp = [to_torch(np.ascontiguousarray(p)) for p in src]
+                hp = [t.pin_memory() if pinned else t for t in hp]
+                self.h_in.append(hp)
+                self.d_in.append([t.to(dev) for t in hp])
+                ho = [torch.empty(s, dtype=tdt(c["bits"])) for s in out_shapes(c)]
+                ho = [t.pin_memory() if pinned else t for t in ho]
+                self.h_out.append(ho)
+                self.d_out.append([torch.empty_like(o, device=dev) for o in ho])
+            torch.cuda.synchronize()
+            self.n = 0
+
+        def dev_frame(self):
+            a, o = self.d_in[self.n % self.nbuf], self.d_out[self.n % self.nbuf]
+            self.n += 1
+            st = lambda t: t.stride(0) * self.bps
+            if self.c["y_only"]:
+                rc = self.eng.process_device_rows(a[0].data_ptr(), st(a[0]), o[0].data_ptr(), st(o[0]), 0, o[0].shape[0], 2, sptr)
+            else:
+                rc = self.eng.process_device(a[0].data_ptr(), st(a[0]), o[0].data_ptr(), st(o[0]), a[1].data_ptr(), st(a[1]),
+                                             a[2].data_ptr(), st(a[2]), o[1].data_ptr(), st(o[1]), o[2].data_ptr(), st(o[2]), 2, sptr)
+            assert rc == 0
+
+        def luma_only(self):
+            a, o = self.d_in[self.n % self.nbuf], self.d_out[self.n % self.nbuf]
+            self.n += 1
+            st = lambda t: t.stride(0) * self.bps
+            assert self.eng.process_device_rows(a[0].data_ptr(), st(a[0]), o[0].data_ptr(), st(o[0]), 0, o[0].shape[0], 2, sptr) == 0
+
+        def time_device(self, fn, frames):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(frames):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        def close(self):
+            self.eng.close()
+
+    class HandlerSession:
+        """Init -> SetRes -> Process* -> Deinit through the RNLHandler_* plugin symbols (vf_raisr.c:146,286-318,334-337) on the
+        HOST planes of a Workload.  Y-only workloads pass small dummy chroma planes: the handler API always takes six planes."""
+
+        def __init__(self, wl, pinned=True):
+            c = wl.c
+            self.wl = wl
+            self.sets = []
+            dummy = None
+            for i in range(wl.nbuf):
+                hin, hout = list(wl.h_in[i]), list(wl.h_out[i])
+                if not pinned:
+                    hin = [t.clone() for t in hin]                # pageable copies of the same frames
+                    hout = [torch.empty_like(t) for t in hout]
+                if c["y_only"]:
+                    if dummy is None:
+                        dummy = [torch.zeros((8, 8), dtype=tdt(c["bits"])) for _ in range(2)], [torch.zeros((16, 16), dtype=tdt(c["bits"])) for _ in range(2)]
+                    hin, hout = hin + dummy[0], hout + dummy[1]
+                vs = [T.VideoDataType(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0) * wl.bps, 0) for t in hin + hout]
+                self.sets.append((vs, [ctypes.byref(v) for v in vs], hin, hout))
+            with quiet_stdout():
+                rc = H.RNLHandler_Init(T.filter_folder(c["folder"]).encode(), c["ratio"], c["bits"], T.VideoRange, 1, T.AVX512, c["passes"], c["mode"])
+                assert rc == 0, hex(rc & 0xffffffff)
+                assert H.RNLHandler_SetRes(*self.sets[0][1]) == 0
+            self.n = 0
+
+        def frame(self):
+            refs = self.sets[self.n % len(self.sets)][1]
+            self.n += 1
+            rc = H.RNLHandler_Process(*refs, T.CountOfBitsChanged)
+            assert rc == 0, hex(rc & 0xffffffff)
+
+        def last_out(self):
+            return self.sets[(self.n - 1) % len(self.sets)][3]
+
+        def close(self):
+            with quiet_stdout():
+                H.RNLHandler_Deinit()
+
+    # ================================== headline: configs[1] ================================================================
+    wl = Workload(HEAD, nbuf=12)
+    for _ in range(args.warmup * FRAMES_PER_STEP):
+        wl.dev_frame()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = eng.launch_count()
+    launches0 = wl.eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
-        for _ in range(FRAMES_PER_STEP):
-            dev_frame(n); n += 1
+    for _ in range(args.steps * FRAMES_PER_STEP):
+        wl.dev_frame()
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count() - launches0
+    launches = wl.eng.launch_count() - launches0
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
 
-    # ---- dominant kernel alone (roofline): luma pass launches, CUDA events on the launching stream -----------
-    for _ in range(FRAMES_PER_STEP):
-        luma_only(n); n += 1
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # dominant kernel alone (roofline): luma pass launches, CUDA events on the launching stream
+    wl.time_device(wl.luma_only, FRAMES_PER_STEP)
     nk = args.steps * FRAMES_PER_STEP
-    k0.record(stream)
-    for _ in range(nk):
-        luma_only(n); n += 1
-    k1.record(stream)
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / nk
+    kern_ms = wl.time_device(wl.luma_only, nk) / nk
     clocks = sampler.stop() if sampler else None
 
-    # ---- end to end through the host-pointer C ABI ("e2e") ---------------------------------------------------
-    for _ in range(max(1, args.warmup)):
-        for _ in range(FRAMES_PER_STEP):
-            host_frame(n); n += 1
+    # end to end through the plugin call with page-locked host planes
+    hs = HandlerSession(wl, pinned=True)
+    for _ in range(max(1, args.warmup) * FRAMES_PER_STEP):
+        hs.frame()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for _ in range(FRAMES_PER_STEP):
-            host_frame(n); n += 1
+    for _ in range(args.steps * FRAMES_PER_STEP):
+        hs.frame()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # the frame the last call filled equals the device-resident result for the same input (not a cached / skipped frame)
+    k = (hs.n - 1) % wl.nbuf
+    wl.n = k
+    wl.dev_frame()
+    torch.cuda.synchronize()
+    for a, b in zip(hs.last_out(), wl.d_out[k]):
+        assert torch.equal(a, b.cpu()), "host-call frame differs from the device-resident frame"
+    hs.close()
 
-    # spot check of the last host frame against nothing but itself being written (non-zero, in range)
-    last = h_out[(n - 1) % NBUF][0]
-    assert int(last.max()) > 0
+    # the same call with pageable planes (what av_frame_get_buffer hands to a software-frame FFmpeg filter)
+    e2e_pageable = None
+    try:
+        hp = HandlerSession(wl, pinned=False)
+        for _ in range(4):
+            hp.frame()
+        barrier()
+        npg = 2 * FRAMES_PER_STEP
+        t0 = time.perf_counter()
+        for _ in range(npg):
+            hp.frame()
+        barrier()
+        e2e_pageable = world * npg / max_over_ranks(time.perf_counter() - t0)
+        hp.close()
+    except Exception as ex:
+        e2e_pageable = {"error": repr(ex)}
+        barrier()
 
     frames_total = world * args.steps * FRAMES_PER_STEP
     value = frames_total / (dev_ms * 1e-3)
     e2e = frames_total / e2e_s
+    numerics = wl.eng.numerics()
+    w, h, oW, oH, bps, BYTES_Y, BYTES_C = geometry(HEAD)
+    wl.close()
+    del wl, hs
+
+    peak, how = measured_peaks()
+
+    # ================================== sub-records of the other configurations (N=1) =======================================
+    sub = {}
+    if world == 1 and not args.no_configs:
+        for name, c in CONFIGS.items():
+            if name == "configs[1]":
+                continue
+            try:
+                ws = Workload(c)
+                nf = 48
+                for _ in range(6):
+                    ws.dev_frame()
+                torch.cuda.synchronize()
+                dms = ws.time_device(ws.dev_frame, nf) / nf
+                kms = ws.time_device(ws.luma_only, nf) / nf
+                hs2 = HandlerSession(ws, pinned=True)
+                for _ in range(4):
+                    hs2.frame()
+                t0 = time.perf_counter()
+                for _ in range(nf):
+                    hs2.frame()
+                es = time.perf_counter() - t0
+                hs2.close()
+                ach = ws.bytes_y / (kms * 1e-3) / 1e9
+                sub[name] = {"workload": c["workload"], "device_ms_per_frame": dms, "frames_per_s": 1e3 / dms,
+                             "luma_passes_ms": kms, "e2e_frames_per_s": nf / es, "frames_timed": nf, "rotating_sets": ws.nbuf,
+                             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                          "algorithmic_bytes_per_frame": ws.bytes_y}}
+                ws.close()
+                del ws, hs2
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                sub[name] = {"workload": c["workload"], "error": repr(ex)}
+
+    # ================================== row-band strong scaling of configs[3] (N>1) =========================================
+    rowband = None
+    if world > 1:
+        try:
+            rowband = rowband_leg(B, torch, dist, dev, local, rank, world, sptr, stream, max_over_ranks, barrier)
+        except Exception as ex:
+            rowband = {"error": repr(ex)}
+
     if rank == 0:
-        peak, how = measured_peaks()
         achieved = BYTES_Y / (kern_ms * 1e-3) / 1e9
         line = {
-            "metric": "frames/sec 1080p->4K 2x RAISR (yuv420p frame: Y pass + chroma resize)",
-            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "sharding": "frame-parallel, no collective",
-                       "l2": "rotating %d distinct frame sets (%.0f MB > 126 MB L2)" % (NBUF, NBUF * BYTES_FRAME / 1e6),
-                       "numerics": "x86-exact (bit-identical to the compiled reference)" if eng.numerics() == 1 else "ieee"},
-            "e2e": {"value": e2e, "unit": "frames/s",
-                    "h2d_bytes_per_step": world * FRAMES_PER_STEP * (IN_W * IN_H + 2 * (IN_W // 2) * (IN_H // 2)),
-                    "d2h_bytes_per_step": world * FRAMES_PER_STEP * (OUT_W * OUT_H + 2 * (OUT_W // 2) * (OUT_H // 2))},
+                       "l2": "rotating 12 distinct frame sets (%.0f MB > 126 MB L2)" % (12 * (BYTES_Y + BYTES_C) / 1e6),
+                       "numerics": "x86-exact (bit-identical to the compiled reference)" if numerics == 1 else "ieee",
+                       "numa": numa},
+            "e2e": {"value": e2e, "unit": "frames/s", "api": "RNLHandler_Process, page-locked host planes",
+                    "h2d_bytes_per_step": world * FRAMES_PER_STEP * (w * h + 2 * (w // 2) * (h // 2)),
+                    "d2h_bytes_per_step": world * FRAMES_PER_STEP * (oW * oH + 2 * (oW // 2) * (oH // 2))},
+            "e2e_pageable": {"value": e2e_pageable, "unit": "frames/s", "api": "RNLHandler_Process, pageable host planes (malloc)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "raisr_pass_kernel<uint8_t>" if os.environ.get("RAISR_CUDA_KERNEL") == "tile" else "raisr_pass_pipe_kernel<uint8_t,4,1>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "raisr_pass_pipe_kernel<uint8_t,4,1>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_Y,
-                         "note": "compute-bound stencil: fp32 issue + shared-memory gather, see DESIGN.md"},
+                         "note": "on-chip bound stencil (shared-memory pipe + issue slots), see DESIGN.md section 4"},
             "cpu_baseline": cpu_baseline_leg() if world == 1 else None,      # timed at N=1 only
         }
+        if sub:
+            line["configs"] = sub
+        if rowband is not None:
+            line["rowband"] = rowband
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
                 tj = json.load(open(traffic_file))
                 line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = "committed ncu capture (%s), not this run" % tj.get("source")
                 # the resources that actually bound the kernel (DESIGN.md section 4): per-launch counts from the committed ncu
                 # capture, rates from this run's kernel time and the SM clock sampled during the timed region
                 mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -363,9 +601,92 @@ def main():
             except Exception:
                 pass
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def rowband_leg(B, torch, dist, dev, local, rank, world, sptr, stream, max_over_ranks, barrier):
+    """BASELINE configs[3] as a strong-scaling job: ONE 4K->8K 10-bit frame (2 passes, mode 2), output rows split into `world`
+    bands (the reference's per-thread band scheme, Raisr.cpp:1738-1779, across GPUs).  Every rank holds the input plane and
+    computes its band with raisr_cuda_process_device_rows; pass 1 is recomputed on the rows pass 2 reaches (overlap-recompute
+    instead of the reference's neighbour wait, Raisr.cpp:905-916); the finished bands are gathered to rank 0 over NCCL.  Before any
+    timing the assembled frame is compared with the single-GPU frame, bit for bit."""
+    spec = importlib.util.spec_from_file_location("raisr_sharding", os.path.join(T.PKG_DIR, "sharding.py"))
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    c = CONFIGS["configs[3]"]
+    w, h, oW, oH, bps, by, bc = geometry(c)
+    eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
+                   numerics=B.NUMERICS_AUTO)
+    eng.set_res(w, h, oW, oH)
+    img = T.synth_frame(w, h, c["bits"], 4321)                               # the same frame on every rank
+    d_in = torch.from_numpy(img.view(np.int16)).to(dev)
+    d_out = torch.zeros((oH, oW), dtype=torch.int16, device=dev)
+    bands = S.row_bands(oH, world)
+    r0, r1 = bands[rank]
+    rows = oH // world
+    assert all(b[1] - b[0] == rows for b in bands), "equal bands expected for the gather"
+    gathered = [torch.empty((rows, oW * 2), dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def band():
+        assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * 2, d_out.data_ptr(), d_out.stride(0) * 2, r0, r1, 2, sptr) == 0
+
+    def gather():
+        dist.gather(d_out[r0:r1].view(torch.uint8), gathered, dst=0)
+
+    # ---- parity first ----
+    band()
+    gather()
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        frame = torch.cat(gathered, 0)
+        full = torch.zeros((oH, oW), dtype=torch.int16, device=dev)
+        assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * 2, full.data_ptr(), full.stride(0) * 2, 0, oH, 2, sptr) == 0
+        torch.cuda.synchronize()
+        parity = bool(torch.equal(frame, full.view(torch.uint8)))
+        assert parity, "row-band frame differs from the single-GPU frame"
+    # ---- timing: band compute alone, then band + gather; device events, max over ranks ----
+    nf = 20
+    for _ in range(3):
+        band()
+        gather()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(nf):
+        band()
+    e1.record(stream)
+    barrier()
+    compute_ms = max_over_ranks(e0.elapsed_time(e1)) / nf
+    e0.record(stream)
+    for _ in range(nf):
+        band()
+        gather()
+    e1.record(stream)
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1)) / nf
+    single_ms = None
+    if rank == 0:
+        full = torch.zeros((oH, oW), dtype=torch.int16, device=dev)
+        fn = lambda: eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * 2, full.data_ptr(), full.stride(0) * 2, 0, oH, 2, sptr)
+        for _ in range(3):
+            fn()
+        e0.record(stream)
+        for _ in range(nf):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / nf
+    barrier()
+    eng.close()
+    # pass-1 rows a band recomputes beyond its own share (mode 2: pass 1 runs at input resolution): +-7 output rows -> /2 + 2
+    lo, hi = max(0, r0 - 7), min(oH, r1 + 7)
+    m0, m1 = max(0, lo // 2 - 2), min(h, -(-hi // 2) + 2)
+    return {"workload": c["workload"], "scaling": "strong", "bands": world, "rows_per_band": rows, "parity": parity,
+            "ms_per_frame": total_ms, "ms_per_frame_compute_only": compute_ms, "single_gpu_ms_per_frame": single_ms,
+            "recompute_rows": {"pass1_rows_per_band": m1 - m0, "own_share": h // world},
+            "collective": "NCCL gather of the finished bands to rank 0 (%d bytes per band); no halo exchange" % (rows * oW * 2)}
 
 
 if __name__ == "__main__":
