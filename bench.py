@@ -349,8 +349,9 @@ def main():
             w, h, oW, oH, bps, by, bc = geometry(c)
             self.bytes_y, self.bytes_frame, self.bps = by, by + bc, bps
             self.nbuf = nbuf or int(min(64, max(2, -(-1.1 * L2_BYTES // (by + bc)))))
-            self.eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
-                                numerics=B.NUMERICS_AUTO)
+            with quiet_stdout():                                 # (two-pass engines print the reference's banner)
+                self.eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
+                                    numerics=B.NUMERICS_AUTO)
             if c["y_only"]:
                 self.eng.set_res(w, h, oW, oH)
             else:
@@ -616,8 +617,9 @@ def rowband_leg(B, torch, dist, dev, local, rank, world, sptr, stream, max_over_
     spec.loader.exec_module(S)
     c = CONFIGS["configs[3]"]
     w, h, oW, oH, bps, by, bc = geometry(c)
-    eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
-                   numerics=B.NUMERICS_AUTO)
+    with quiet_stdout():
+        eng = B.Engine(T.filter_folder(c["folder"]), c["ratio"], c["bits"], T.VideoRange, c["passes"], c["mode"], device=local,
+                       numerics=B.NUMERICS_AUTO)
     eng.set_res(w, h, oW, oH)
     img = T.synth_frame(w, h, c["bits"], 4321)                               # the same frame on every rank
     d_in = torch.from_numpy(img.view(np.int16)).to(dev)

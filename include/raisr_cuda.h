@@ -28,6 +28,13 @@ enum {
     RAISR_NUMERICS_X86_IF_AVAILABLE = 2  /* X86 when the tables are linked in, else IEEE (what RNLHandler_Init asks for)     */
 };
 
+/* special values of raisr_cuda_config.device */
+enum {
+    RAISR_CUDA_DEVICE_CURRENT = -1,         /* the calling thread's current device, re-selected on every call            */
+    RAISR_CUDA_DEVICE_CALLER_CONTEXT = -2   /* driver-API interop (FFmpeg's AVCUDADeviceContext): the engine runs in the
+                                               CUcontext the caller has made current around EVERY call and never switches  */
+};
+
 typedef struct raisr_cuda_config {
     const char *model_path;    /* filter folder: filterbin_2_<bits>[_2], Qfactor_{str,coh}bin_2_<bits>[_2], config            */
     float ratio;               /* 2.0 or 1.5                                                                                  */
@@ -35,7 +42,7 @@ typedef struct raisr_cuda_config {
     int range_type;            /* 1 = video range, 2 = full range (RangeType)                                                 */
     unsigned passes;           /* 1 or 2                                                                                      */
     unsigned two_pass_mode;    /* 1: upscale in pass 1; 2: upscale in pass 2                                                  */
-    int device;                /* CUDA device ordinal, -1 = current device                                                    */
+    int device;                /* CUDA device ordinal, or RAISR_CUDA_DEVICE_CURRENT / RAISR_CUDA_DEVICE_CALLER_CONTEXT          */
     int numerics;              /* RAISR_NUMERICS_*                                                                            */
     int keep_hash;             /* != 0: keep the per-pass bucket planes for raisr_cuda_read_hash (parity tests)               */
 } raisr_cuda_config;

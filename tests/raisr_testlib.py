@@ -27,9 +27,13 @@ class VideoDataType(C.Structure):  # RaisrDefaults.h:13-20
                 ("step", C.c_uint), ("bitShift", C.c_uint)]
 
 
+DATA_DIR = os.path.join(ROOT, "data")
+
+
 def filter_folder(name):
-    """'filters_2x/filters_lowres' -> absolute path of the staged copy (oracle/_ref) or the reference tree."""
-    for base in (REF_DIR, "/root/reference"):
+    """'filters_2x/filters_lowres' -> absolute path of the staged copy (data/: the reference's trained tables, consumed
+    read-only like any caller-supplied model folder) or the reference tree."""
+    for base in (DATA_DIR, "/root/reference"):
         p = os.path.join(base, name)
         if os.path.isdir(p):
             return p

@@ -120,6 +120,7 @@ struct raisr_cuda_engine {
     int bps = 1;                    // bytes per sample
     int lo = 0, hi = 255;
     int device = 0;
+    bool bind_device = true;        // false (cfg.device == RAISR_CUDA_DEVICE_CALLER_CONTEXT): run in whatever CUDA context the caller made current, never switch
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
     bool no_memops = false;         // RAISR_CUDA_NO_MEMOPS=1 (or CUDA_LAUNCH_BLOCKING=1): no in-kernel flag waits, everything in plain stream order
@@ -452,6 +453,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     }
 
     auto fail = [&](int code) { raisr_cuda_destroy(e); return code; };
+    e->bind_device = cfg->device != RAISR_CUDA_DEVICE_CALLER_CONTEXT;
     if (cfg->device >= 0) {
         if (cudaSetDevice(cfg->device) != cudaSuccess) {
             std::cout << "[RAISR ERROR] cannot select CUDA device " << cfg->device << std::endl;
@@ -547,7 +549,7 @@ int raisr_cuda_set_res(raisr_cuda_engine *e, unsigned in_w, unsigned in_h, unsig
                        unsigned in_cw, unsigned in_ch, unsigned out_cw, unsigned out_ch)
 {
     if (!e || !in_w || !in_h || !out_w || !out_h) return RNLErrorBadParameter;
-    CUDA_OK(cudaSetDevice(e->device));
+    if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     e->in_w = in_w; e->in_h = in_h; e->out_w = out_w; e->out_h = out_h;
     e->in_cw = in_cw; e->in_ch = in_ch; e->out_cw = out_cw; e->out_ch = out_ch;
     // the resize spec of the reference maps {inW, (int)(outH / ratio)} -> {outW, outH} (Raisr.cpp:1801-1803)
@@ -591,7 +593,7 @@ int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_
     if (!e || !e->have_res || !in_y || !out_y || row0 >= row1 || row1 > (unsigned)e->out_h) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
     e->blending = blending;
-    CUDA_OK(cudaSetDevice(e->device));
+    if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (unsigned i = 0; i < e->cfg.passes; ++i)
         if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
@@ -608,7 +610,7 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
         // one launch per pass: the chroma planes ride along with the (first) luma launch
         if (check_blending(blending)) return RNLErrorBadParameter;
         e->blending = blending;
-        CUDA_OK(cudaSetDevice(e->device));
+        if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
         for (unsigned i = 0; i < e->cfg.passes; ++i)
             if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
         const ChromaJob cj{{in_u, in_v}, {in_u_step, in_v_step}, {out_u, out_v}, {out_u_step, out_v_step}, nullptr, 0, nullptr};
@@ -670,6 +672,8 @@ int process_host_tile(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
                                       cudaMemcpyDeviceToHost, e->stream_uv));
     }
     CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, e->in_h, cudaMemcpyHostToDevice, e->stream));
+    for (unsigned i = 0; i < e->cfg.passes; ++i)
+        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
     int rc = run_luma(e, e->d_in[0].ptr, e->d_in[0].pitch, e->d_out[0].ptr, e->d_out[0].pitch, 0, e->out_h, e->stream);
     if (rc) return rc;
     CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
@@ -816,7 +820,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     if (!e || !e->have_res || !in_y || !out_y) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
     e->blending = blending;
-    CUDA_OK(cudaSetDevice(e->device));
+    if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
     int rc = e->use_pipe ? process_host_pipe(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma)
                          : process_host_tile(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma);
@@ -832,7 +836,7 @@ int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size
 {
     if (!e || pass < 0 || pass > 1 || !e->d_hash[pass] || !host_out) return RNLErrorBadParameter;
     if (count != (size_t)e->hash_w[pass] * e->hash_h[pass]) return RNLErrorBadParameter;
-    CUDA_OK(cudaSetDevice(e->device));
+    if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(host_out, e->d_hash[pass], count * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return RNLErrorNone;
@@ -845,7 +849,7 @@ int raisr_cuda_numerics(const raisr_cuda_engine *e) { return e ? e->cfg.numerics
 void raisr_cuda_destroy(raisr_cuda_engine *e)
 {
     if (!e) return;
-    cudaSetDevice(e->device);
+    if (e->bind_device) cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     if (e->timing && e->t_n) std::cout << "[RAISR TIMING] frames " << e->t_n << " luma H2D " << 1e3 * e->t_h2d / e->t_n << " us, memset+kernel " << 1e3 * e->t_kern / e->t_n << " us" << std::endl;
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_hash[i]); }
