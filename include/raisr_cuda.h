@@ -25,7 +25,11 @@ typedef struct raisr_cuda_engine raisr_cuda_engine;
 enum {
     RAISR_NUMERICS_IEEE = 0,   /* sqrt.rn / div.rn: the specification in oracle/raisr_oracle.c (ORACLE_SQRT_IEEE)          */
     RAISR_NUMERICS_X86  = 1,   /* reproduces the compiled reference: vrcp14ps(vrsqrt14ps(x)) etc. via lookup tables          */
-    RAISR_NUMERICS_X86_IF_AVAILABLE = 2  /* X86 when the tables are linked in, else IEEE (what RNLHandler_Init asks for)     */
+    RAISR_NUMERICS_X86_IF_AVAILABLE = 2, /* X86 when the tables are linked in, else IEEE (what RNLHandler_Init asks for)     */
+    RAISR_NUMERICS_FP16_FILTER = 3       /* OPT-IN fast numerics: hash as in mode 2 (buckets identical to the fp32 path), the 121-tap
+                                            filter in half precision (coefficients rounded to binary16, HMUL2/HFMA2 chains, fp32 tree);
+                                            the counterpart of the reference's asm=avx512fp16 (Raisr_AVX512FP16.cpp:227-242).  8/10 bit
+                                            only.  Y is NOT bit-identical to the fp32 path: see DESIGN.md for the measured error.       */
 };
 
 /* special values of raisr_cuda_config.device */

@@ -222,3 +222,39 @@ def test_randomness_blending_vs_oracle(folder, ratio, bits, passes, mode, size, 
     m2 = T.OracleModel(f, bits, True, T.VideoRange, sm, T.Randomness) if passes == 2 else None
     ref = T.oracle_process_y(img, oW, oH, m1, m2, passes, mode)
     assert np.array_equal(out, ref), "Y differs on %d px" % (out != ref).sum()
+
+
+# ---- two-pass configurations in ONE persistent launch (chained passes) ------------------------------------------------------
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size", [
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1, (1000, 600)),          # mode 1: exact-2x upscale in pass 1 -> plain pass 2
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (960, 540)),          # mode 2: pass 1 at input resolution -> upscaling pass 2
+    ("filters_1.5x/filters_denoise", 1.5, 8, 2, 2, (640, 360)),         # one pixel type, axis-map upscale in pass 2
+    ("filters_2x/filters_highres", 2.0, 8, 2, 1, (150, 66)),            # fewer tiles than SMs: CTAs without a pass-1 tile
+])
+def test_chained_passes_equal_one_launch_per_pass(folder, ratio, bits, passes, mode, size, monkeypatch):
+    """Default: both passes in one cooperative launch (pass-2 tiles wait for the pass-1 tile rows they read).  Must be bit-identical
+    to RAISR_CUDA_CHAIN=0 (a kernel boundary between the passes) -- buckets of both passes and Y -- and use a single launch."""
+    w, h = size
+    f = T.filter_folder(folder)
+    img = T.synth_frame(w, h, bits, seed=909 + w, kind="mix")
+    oW, oH = int(w * ratio), int(h * ratio)
+
+    def run():
+        eng = B.Engine(f, ratio, bits, T.VideoRange, passes, mode, numerics=B.NUMERICS_AUTO, keep_hash=True)
+        eng.set_res(w, h, oW, oH)
+        out = np.zeros((oH, oW), img.dtype)
+        n0 = eng.launch_count()
+        for _ in range(3):                                           # the tile-row counters are re-armed per frame
+            out[...] = 0
+            assert eng.process_host(img, out) == 0
+        n = (eng.launch_count() - n0) // 3
+        hs = [eng.read_hash(i, w if (mode == 2 and i == 0) else oW, h if (mode == 2 and i == 0) else oH) for i in range(2)]
+        eng.close()
+        return out, hs, n
+
+    chained, hc, nc = run()
+    monkeypatch.setenv("RAISR_CUDA_CHAIN", "0")
+    split, hs, ns = run()
+    assert ns == 2 and nc == 1, "launches per frame: chained %d, split %d" % (nc, ns)
+    assert all(np.array_equal(a, b) for a, b in zip(hc, hs)), "buckets differ"
+    assert np.array_equal(chained, split), "Y differs on %d px" % (chained != split).sum()

@@ -20,8 +20,10 @@
 
 #include "raisr/RaisrDefaults.h"
 #include "raisr_cuda.h"
+#include <cuda_fp16.h>
+
 #include "raisr_kernels.cuh"
-#include "raisr_pipe_kernel.cuh"
+#include "raisr_launch.h"
 #include "raisr_model.h"
 #include "x86_tables.h"
 
@@ -129,7 +131,11 @@ struct raisr_cuda_engine {
     bool band_pipeline = true;      // luma D2H in row bands under the kernel; RAISR_CUDA_NO_BAND_PIPELINE=1 disables
     bool use_pipe = true;           // persistent warp-specialised kernel; RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (cross-check)
     float gw[11][6] = {};           // folded Gaussian weights of this engine's bit depth (copied into every launch's parameters)
-    unsigned attr_set = 0;          // kernel instantiations whose dynamic shared-memory opt-in has been set on e->device (bit per instantiation)
+    bool filter_fp16 = false;       // RAISR_NUMERICS_FP16_FILTER: half-precision filter stage (opt-in, Y not bit-identical); the hash keeps cfg.numerics
+    bool chain_passes = true;       // two-pass configurations in one persistent launch; RAISR_CUDA_CHAIN=0: one launch per pass
+    bool coop_launch = false;       // device supports cooperative launches (needed by the chained launch)
+    unsigned *d_rows_done = nullptr; int rows_done_cap = 0;   // chained launch: finished tiles per tile row of the first pass
+    void *d_filters16[2] = {nullptr, nullptr};                 // fp16 copies of the filter tables (filter_fp16 only)
     float *d_filters[2] = {nullptr, nullptr};
     void *d_lut[4] = {nullptr, nullptr, nullptr, nullptr};   // rsqrt14 runs, rcp14 runs, rsqrtps, rcpps
     // geometry
@@ -187,47 +193,34 @@ void fill_weights(raisr_cuda_engine *e, unsigned bits)
     }
 }
 
-template <typename PixT, int PT, int UPS>
-int launch_pass_k(raisr_cuda_engine *e, const PassParams &q, dim3 grid, cudaStream_t s)
-{
-    // The >48 KB dynamic shared-memory opt-in is a per-device function attribute: tracked per engine (an engine lives on one
-    // device), never in process-global state.
-    const unsigned bit = 1u << ((sizeof(PixT) == 2 ? 6 : 0) + (PT == 4 ? 3 : 0) + UPS);
-    if (!(e->attr_set & bit)) {
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        CUDA_OK(cudaFuncSetAttribute(raisr_pass_pipe_kernel<PixT, PT, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES));
-        e->attr_set |= bit;
-    }
-    if (e->use_pipe) {
-        // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
-        const int ntiles = (int)(grid.x * grid.y);
-        if (q.chroma_n) e->last_chroma_ctas = std::min(ntiles, e->num_sms);
-        raisr_pass_pipe_kernel<PixT, PT, UPS><<<std::min(ntiles, e->num_sms), NTP, PIPE_SMEM_BYTES, s>>>(q);
-    } else {
-        raisr_pass_kernel<PixT, PT, UPS><<<grid, NT, SMEM_BYTES, s>>>(q);
-    }
-    CUDA_OK(cudaGetLastError());
-    e->launches++;
-    return 0;
-}
+// ---- launch planning ------------------------------------------------------------------------------------------------
+// One pass, planned: tile height, grid, band geometry, upscale flavour.  The kernels live in their own translation units
+// (raisr_launch.h); this file only fills parameter blocks.
+struct PassPlan {
+    PassParams q;
+    dim3 grid;               // tiles (x) by tile rows (y)
+    int ups = 0;             // 0 none, 1 exact 2x, 2 axis maps
+};
 
-template <typename PixT>
-int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
+PassPlan plan_pass(raisr_cuda_engine *e, const PassParams &p)
 {
-    // tile height: the largest even th <= TH_MAX whose tile count still fits the same number of waves (one CTA per SM)
-    PassParams q = p;
+    // tile height: the largest even th <= the kernel's maximum whose tile count still fits the same number of waves (one CTA per SM)
+    PassPlan pl;
+    PassParams &q = pl.q;
+    q = p;
+    const int bpsx = e->bps;
     const int rows = p.row1 - p.row0, gx = (p.W + TW - 1) / TW;
-    const int thmax = e->use_pipe ? PTH_MAX : TH_MAX;
+    const int thmax = e->use_pipe ? pipe_tile_h_max() : TH_MAX;
     int ny = (rows + thmax - 1) / thmax;
     const int waves = (gx * ny + e->num_sms - 1) / e->num_sms;
     while ((long long)gx * (ny + 1) <= (long long)waves * e->num_sms && 2 * (ny + 1) <= rows) ++ny;
     q.tile_h = std::min(thmax, (((rows + ny - 1) / ny) + 1) & ~1);
-    const dim3 grid(gx, (rows + q.tile_h - 1) / q.tile_h);
+    pl.grid = dim3(gx, (rows + q.tile_h - 1) / q.tile_h);
     // tile rows of the last round of the persistent kernel (they finish together, at the very end): written in place into the
     // caller's pinned plane when there is one, so that no copy remains after the kernel; the bands cover the rows above
-    int banded_rows = (int)grid.y;
+    int banded_rows = (int)pl.grid.y;
     if (q.out_tail && e->use_pipe) {
-        banded_rows = std::max(0, (int)grid.y - ((e->num_sms + gx - 1) / gx + 1));
+        banded_rows = std::max(0, (int)pl.grid.y - ((e->num_sms + gx - 1) / gx + 1));
         q.tail_row0 = p.row0 + banded_rows * q.tile_h;
     } else {
         q.out_tail = nullptr;
@@ -244,23 +237,68 @@ int launch_pass_t(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
             e->band_tiles[b] = (unsigned)(tiles_y * gx);
         }
     }
-    q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch | reinterpret_cast<uintptr_t>(q.out_tail) | (q.out_tail ? q.out_tail_pitch : 0)) % (4 * sizeof(PixT))) == 0;
+    q.vec_store = ((reinterpret_cast<uintptr_t>(p.out) | p.out_pitch | reinterpret_cast<uintptr_t>(q.out_tail) | (q.out_tail ? q.out_tail_pitch : 0)) % (4 * bpsx)) == 0;
     // 2x fast path: exact factor 2 in both axes and even band origin
     const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
-    const int ups = !p.upscale ? 0 : (fast2x ? 1 : 2);
-    if (p.ptypes == 4) {
-        if (ups == 0) return launch_pass_k<PixT, 4, 0>(e, q, grid, s);
-        if (ups == 1) return launch_pass_k<PixT, 4, 1>(e, q, grid, s);
-        return launch_pass_k<PixT, 4, 2>(e, q, grid, s);
-    }
-    if (ups == 0) return launch_pass_k<PixT, 1, 0>(e, q, grid, s);
-    if (ups == 1) return launch_pass_k<PixT, 1, 1>(e, q, grid, s);
-    return launch_pass_k<PixT, 1, 2>(e, q, grid, s);
+    pl.ups = !p.upscale ? 0 : (fast2x ? 1 : 2);
+    return pl;
 }
 
+int cuda_failed(int err, const char *what)
+{
+    std::cout << "[RAISR ERROR] CUDA failure: " << cudaGetErrorString((cudaError_t)err) << " (" << what << ")" << std::endl;
+    return RNLErrorInsufficientResources;
+}
+
+int launch_frame(raisr_cuda_engine *e, const FrameLaunch &fl)
+{
+    if (e->bps == 1) return e->filter_fp16 ? launch_frame_pipe<uint8_t, true>(fl) : launch_frame_pipe<uint8_t, false>(fl);
+    return e->filter_fp16 ? launch_frame_pipe<uint16_t, true>(fl) : launch_frame_pipe<uint16_t, false>(fl);
+}
+
+// one pass = one launch
 int launch_pass(raisr_cuda_engine *e, const PassParams &p, cudaStream_t s)
 {
-    return e->bps == 1 ? launch_pass_t<uint8_t>(e, p, s) : launch_pass_t<uint16_t>(e, p, s);
+    PassPlan pl = plan_pass(e, p);
+    int err;
+    if (e->use_pipe) {
+        // persistent warp-specialised kernel: one CTA per SM walks the tiles (producer/consumer warp groups)
+        FrameLaunch fl;
+        fl.a = pl.q; fl.ups_a = pl.ups; fl.stream = s;
+        fl.grid = std::min((int)(pl.grid.x * pl.grid.y), e->num_sms);
+        if (pl.q.chroma_n) e->last_chroma_ctas = fl.grid;
+        err = launch_frame(e, fl);
+    } else {
+        err = e->bps == 1 ? launch_pass_tile<uint8_t>(pl.q, pl.ups, pl.grid, s) : launch_pass_tile<uint16_t>(pl.q, pl.ups, pl.grid, s);
+    }
+    if (err) return cuda_failed(err, "pass launch");
+    e->launches++;
+    return 0;
+}
+
+// Both passes of a two-pass configuration in ONE persistent launch (Raisr.cpp:896-927 runs them back to back per band, with
+// a neighbour wait, :905-916): the CTAs walk pass 1's tiles and carry straight on into pass 2's; a pass-2 tile waits for the
+// pass-1 tile rows that cover its input rows (counters in d_rows_done).  The intermediate plane stays in L2.
+// Returns -1 when this pair has no chained instantiation or the device cannot launch it cooperatively (-> two launches).
+int launch_chained(raisr_cuda_engine *e, const PassParams &p1, const PassParams &p2, cudaStream_t s)
+{
+    if (!e->use_pipe || !e->chain_passes || !e->coop_launch || !e->d_rows_done) return -1;
+    PassPlan a = plan_pass(e, p1), b = plan_pass(e, p2);
+    if ((int)a.grid.y > e->rows_done_cap) return -1;
+    FrameLaunch fl;
+    fl.a = a.q; fl.b = b.q; fl.two = true; fl.ups_a = a.ups; fl.ups_b = b.ups; fl.stream = s;
+    fl.a.rows_done = e->d_rows_done;
+    fl.b.dep_done = e->d_rows_done;
+    fl.b.dep_gx = (int)a.grid.x; fl.b.dep_ny = (int)a.grid.y;
+    fl.b.dep_row0 = a.q.row0; fl.b.dep_row1 = a.q.row1; fl.b.dep_th = a.q.tile_h;
+    fl.grid = std::min((int)(a.grid.x * a.grid.y + b.grid.x * b.grid.y), e->num_sms);
+    if (fl.a.chroma_n) e->last_chroma_ctas = fl.grid;          // every CTA of the grid takes a share of the chroma planes (and bumps chroma_done once)
+    if (cudaMemsetAsync(e->d_rows_done, 0, sizeof(unsigned) * a.grid.y, s) != cudaSuccess) return cuda_failed((int)cudaGetLastError(), "rows_done memset");
+    const int err = launch_frame(e, fl);
+    if (err == (int)cudaErrorInvalidDeviceFunction || err == (int)cudaErrorCooperativeLaunchTooLarge) { cudaGetLastError(); return -1; }
+    if (err) return cuda_failed(err, "chained launch");
+    e->launches++;
+    return 0;
 }
 
 int launch_resize(raisr_cuda_engine *e, const void *in, size_t in_pitch, void *out, size_t out_pitch, cudaStream_t s)
@@ -279,7 +317,7 @@ int launch_resize(raisr_cuda_engine *e, const void *in, size_t in_pitch, void *o
 void pass_common(const raisr_cuda_engine *e, int pass_idx, int W, PassParams *p)
 {
     const PassModel &pm = e->model.pass[pass_idx];
-    p->filters = e->d_filters[pass_idx];
+    p->filters = e->filter_fp16 ? static_cast<const float *>(e->d_filters16[pass_idx]) : e->d_filters[pass_idx];
     p->ptypes = pm.ptypes;
     p->nbuckets = pm.buckets;
     p->qstr0 = pm.qstr[0]; p->qstr1 = pm.qstr[1];
@@ -378,7 +416,9 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     p2.band_done = band_done; p2.out_tail = out_tail; p2.out_tail_pitch = out_tail_step;
     p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_split_row = in_split_row;
     set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
-    int rc = launch_pass(e, p1, s);
+    int rc = launch_chained(e, p1, p2, s);       // both passes in one persistent launch where possible
+    if (rc >= 0) return rc;
+    rc = launch_pass(e, p1, s);
     if (rc) return rc;
     return launch_pass(e, p2, s);
 }
@@ -468,6 +508,25 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *nm = std::getenv("RAISR_CUDA_NO_MEMOPS")) e->no_memops = std::atoi(nm) != 0;
     if (const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING")) e->no_memops = e->no_memops || std::atoi(lb) != 0;
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
+    if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0;
+    {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+        e->coop_launch = coop != 0;
+    }
+    if (e->cfg.numerics == RAISR_NUMERICS_FP16_FILTER) {
+        // opt-in fast numerics: fp16 filter stage on top of the exact fp32 hash (buckets stay those of the fp32 path)
+        if (cfg->bit_depth > 10) {
+            std::cout << "[RAISR ERROR] the fp16 filter stage supports 8 and 10 bit only (16-bit samples overflow half precision)" << std::endl;
+            return fail(RNLErrorBadParameter);
+        }
+        if (!e->use_pipe) {
+            std::cout << "[RAISR ERROR] the fp16 filter stage exists in the pipelined kernel only" << std::endl;
+            return fail(RNLErrorBadParameter);
+        }
+        e->filter_fp16 = true;
+        e->cfg.numerics = RAISR_NUMERICS_X86_IF_AVAILABLE;
+    }
     if (std::getenv("RAISR_CUDA_TIMING")) { e->timing = true; for (auto &ev : e->tev) cudaEventCreate(&ev); }
     for (unsigned i = 0; i < passes; ++i) {
         // device layout: [ptype][bucket][128], each row permuted so that the 8 lanes working on a pixel read 128
@@ -489,6 +548,13 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         if (cudaMalloc(&e->d_filters[i], bytes) != cudaSuccess ||
             cudaMemcpy(e->d_filters[i], dev.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(RNLErrorInsufficientResources);
+        if (e->filter_fp16) {                        // same layout, coefficients rounded to nearest-even binary16
+            std::vector<__half> dev16(dev.size());
+            for (size_t k = 0; k < dev.size(); ++k) dev16[k] = __float2half_rn(dev[k]);
+            if (cudaMalloc(&e->d_filters16[i], dev16.size() * sizeof(__half)) != cudaSuccess ||
+                cudaMemcpy(e->d_filters16[i], dev16.data(), dev16.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(RNLErrorInsufficientResources);
+        }
     }
     X86Tables xt{};
     const bool have_tables = x86_tables(&xt);
@@ -511,6 +577,15 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
                 return fail(RNLErrorInsufficientResources);
     }
     fill_weights(e, cfg->bit_depth);
+    {
+        // > 48 KB dynamic shared memory is a per-device function attribute: set for this engine's kernels on this engine's device
+        int err = e->bps == 1 ? prepare_pass_tile<uint8_t>() : prepare_pass_tile<uint16_t>();
+        if (!err) {
+            if (e->bps == 1) err = e->filter_fp16 ? prepare_frame_pipe<uint8_t, true>() : prepare_frame_pipe<uint8_t, false>();
+            else err = e->filter_fp16 ? prepare_frame_pipe<uint16_t, true>() : prepare_frame_pipe<uint16_t, false>();
+        }
+        if (err) { cuda_failed(err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); return fail(RNLErrorInsufficientResources); }
+    }
     // flags and counters shared with the running kernel: all start at zero (the D2H stream waits for RUNNING totals of band_done)
     if (cudaMalloc(&e->d_chroma_ready, 2 * sizeof(unsigned)) != cudaSuccess || cudaMemset(e->d_chroma_ready, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&e->d_in_ready, sizeof(unsigned)) != cudaSuccess || cudaMemset(e->d_in_ready, 0, sizeof(unsigned)) != cudaSuccess ||
@@ -573,6 +648,11 @@ int raisr_cuda_set_res(raisr_cuda_engine *e, unsigned in_w, unsigned in_h, unsig
     if (e->cfg.passes == 2) {
         const bool mode2 = e->cfg.two_pass_mode == 2;       // intermediate is LR-sized in mode 2 (Raisr.cpp:1703-1723)
         if (e->d_mid.alloc(mode2 ? in_w : out_w, mode2 ? in_h : out_h, e->bps)) return RNLErrorInsufficientResources;
+    }
+    cudaFree(e->d_rows_done); e->d_rows_done = nullptr; e->rows_done_cap = 0;
+    if (e->cfg.passes == 2) {
+        e->rows_done_cap = (int)std::max(in_h, out_h) / 2 + 2;          // tile rows of a pass (tiles are at least 2 rows high)
+        CUDA_OK(cudaMalloc(&e->d_rows_done, sizeof(unsigned) * e->rows_done_cap));
     }
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_hash[i]); e->d_hash[i] = nullptr; }
     if (e->cfg.keep_hash) {
@@ -844,7 +924,7 @@ int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size
 
 unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e) { return e ? e->launches : 0; }
 
-int raisr_cuda_numerics(const raisr_cuda_engine *e) { return e ? e->cfg.numerics : -1; }
+int raisr_cuda_numerics(const raisr_cuda_engine *e) { return e ? (e->filter_fp16 ? (int)RAISR_NUMERICS_FP16_FILTER : e->cfg.numerics) : -1; }
 
 void raisr_cuda_destroy(raisr_cuda_engine *e)
 {
@@ -852,7 +932,8 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     if (e->bind_device) cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     if (e->timing && e->t_n) std::cout << "[RAISR TIMING] frames " << e->t_n << " luma H2D " << 1e3 * e->t_h2d / e->t_n << " us, memset+kernel " << 1e3 * e->t_kern / e->t_n << " us" << std::endl;
-    for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_hash[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_filters16[i]); cudaFree(e->d_hash[i]); }
+    cudaFree(e->d_rows_done);
     for (int i = 0; i < 4; ++i) cudaFree(e->d_lut[i]);
     for (int i = 0; i < 3; ++i) { e->d_in[i].release(); e->d_out[i].release(); }
     e->d_mid.release();

@@ -48,6 +48,12 @@ struct PassParams {
     unsigned in_seq;         // sequence number of this frame
     int in_split_row;        // input rows >= in_split_row are valid once *in_ready == in_seq (rows above: stream order)
     unsigned *err_flag;      // optional: set to 1 when an in-kernel flag wait times out (a copy the kernel waits for never landed)
+    // chained two-pass launch (pipelined kernel): the first pass counts finished tiles per tile row, the second waits for the tile
+    // rows of the first that cover the input rows it reads
+    unsigned *rows_done;     // optional (first pass): [tile rows] finished tiles, zeroed by the host before the launch
+    const unsigned *dep_done; // second pass: the first pass's rows_done
+    int dep_gx, dep_ny;      //   tiles per tile row / tile rows of the first pass
+    int dep_row0, dep_row1, dep_th;   // its output rows [dep_row0, dep_row1) and tile height
     unsigned *band_done;     // optional: per row band, the number of finished tiles (host-side copy pipeline)
     int band_tiles_y;        // tile rows per band
     void *out_tail;          // optional: output rows >= tail_row0 go here instead (the caller's pinned plane, written in place:

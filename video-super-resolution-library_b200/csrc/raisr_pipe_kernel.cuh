@@ -73,6 +73,38 @@ template <int IMM> __device__ __forceinline__ void lds_f32x2x2(unsigned a, f32x2
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(lo), "=l"(hi) : "r"(a), "n"(IMM));
 }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <int IMM> __device__ __forceinline__ void lds_b32x2(unsigned a, unsigned &lo, unsigned &hi)
+{
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(lo), "=r"(hi) : "r"(a), "n"(IMM));
+}
+
+// Half-precision pairs of the opt-in fp16 filter stage: IEEE binary16, round to nearest even (HMUL2 / HFMA2: one rounding per
+// operation, like the vmulph / vfmadd...ph of the reference's AVX512-FP16 dot product, Raisr_AVX512FP16.cpp:227-242).
+__device__ __forceinline__ unsigned f2h2(float lo, float hi) { unsigned r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+__device__ __forceinline__ unsigned hmul2(unsigned a, unsigned b) { unsigned r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ unsigned hfma2(unsigned a, unsigned b, unsigned c) { unsigned r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ void h2f2(unsigned h2, float &lo, float &hi)
+{
+    asm("{\n .reg .b16 l, h;\n mov.b32 {l, h}, %2;\n cvt.f32.f16 %0, l;\n cvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(h2));
+}
+
+// dot8() of the fp16 filter stage (overlap columns, rare path): frow = the pixel's 256-byte row of half-precision coefficients in
+// the same lane-permuted order; the chain pair (2q, 2q+1) runs in half2, the 16 chain sums are added in fp32 (tree8).
+__device__ __forceinline__ float dot8_h(const float *sp, const char *frow, const int (&off)[8][2], int q)
+{
+    unsigned acc = 0u;
+    const uint2 *f2 = reinterpret_cast<const uint2 *>(frow) + q;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const uint2 f = f2[n * 8];
+        const unsigned p01 = f2h2(sp[off[2 * n][0]], sp[off[2 * n][1]]), p23 = f2h2(sp[off[2 * n + 1][0]], sp[off[2 * n + 1][1]]);
+        acc = (n == 0) ? hmul2(p01, f.x) : hfma2(p01, f.x, acc);
+        acc = hfma2(p23, f.y, acc);
+    }
+    float a0, a1;
+    h2f2(acc, a0, a1);
+    return tree8(a0, a1, q);
+}
 
 // One sample of the upscaled plane for the producer's ring (out-of-frame coordinates are clamped: such samples only
 // feed pixels that are never hashed).
@@ -120,10 +152,32 @@ __device__ __forceinline__ void spin_wait_flag(const unsigned *flag, unsigned se
     }
 }
 
+// same, for a counter that only grows during the launch: wait until *flag >= need
+__device__ __forceinline__ void spin_wait_flag_geq(const unsigned *flag, unsigned need, unsigned *err)
+{
+    unsigned long long t0 = 0;
+    for (unsigned n = 1;; ++n) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= need) return;
+        if ((n & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            volatile unsigned *verr = err;
+            const bool failed = verr && *verr != 0;
+            if (failed || t - t0 > 2000000000ull) {
+                if (verr) { *verr = 1u; __threadfence_system(); }
+                return;
+            }
+        }
+    }
+}
+
 // Split H2D: the lower part of the input plane (rows >= in_split_row) may still be on its way (own stream, flagged).  Called by
 // a warp group (its leader spins, the group's named barrier publishes the result) before the first access to such rows.  Not inlined, scalar arguments only (taking the
 // address of the kernel parameter block would move every access to it into local memory).
-__device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader, int bar, int count)
+static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader, int bar, int count)
 {
     if (leader) spin_wait_flag(flag, seq, err);
     group_sync(bar, count);
@@ -237,26 +291,521 @@ __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int 
     }
 }
 
-template <typename PixT, int PT, int UPS>
-__global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParams p)
+
+// ---- state a thread carries across the passes of ONE launch ------------------------------------------------------------
+struct PipeCarry {
+    int iter;                // tiles this CTA has started so far (bucket tile buffer = iter & 1; FULL/EMPTY hand-offs run on across passes)
+    int total_iters;         // tiles this CTA walks in the whole launch (all passes)
+    unsigned gk;             // producers: running chunk number (chain buffer = gk & 1)
+    unsigned nload;          // filter warps: filter-slice loads issued so far (mbarrier phase)
+};
+
+// Tiles of a pass and this CTA's first one.  A launch walks the tiles of pass A and then those of pass B as ONE round-robin
+// sequence T = blockIdx.x + k * gridDim.x (T < tiles(A): tile T of pass A, else tile T - tiles(A) of pass B): no bubble between
+// the passes, every CTA simply keeps going.
+__device__ __forceinline__ int pass_tiles(const PassParams &p)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *sS = reinterpret_cast<float *>(smem_raw + POFF_S);
-    float *sHR = reinterpret_cast<float *>(smem_raw + POFF_HR);
-    float *sF = reinterpret_cast<float *>(smem_raw + POFF_F);
+    return ((p.W + TW - 1) / TW) * ((p.row1 - p.row0 + p.tile_h - 1) / p.tile_h);
+}
+
+// Input rows [lo, hi] (of the pass's input plane) a tile with output rows [y0, y0 + th) reads: the +-7 halo, through the upscale.
+template <int UPS>
+__device__ __forceinline__ void tile_input_rows(const PassParams &p, int y0, int th, int &lo, int &hi)
+{
+    const int yfirst = max(0, y0 - 8), ylast = min(p.H - 1, y0 + th + 6);
+    if (UPS == 0) { lo = yfirst; hi = ylast; }
+    else if (UPS == 1) { lo = max(0, (yfirst >> 1) - 1); hi = (ylast >> 1) + 1; }
+    else { lo = max(0, (__ldg(p.ymap + yfirst) >> 1) - 1); hi = (__ldg(p.ymap + ylast) >> 1) + 1; }
+}
+
+// Chained second pass: its input plane is the first pass's output, produced by the SAME launch.  The first pass counts finished
+// tiles per tile row (dep_done, zeroed by the host before the launch); before a group reads input rows [lo, hi] its leader waits
+// until every tile row of pass A that covers them is complete (bounded spin, ld.acquire.gpu: also drops stale L1 lines), the
+// group's named barrier publishes that.  `known` = tile rows [0, known) already seen complete (tiles come in row order).
+static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigned need, int ty_hi, int known, unsigned *err, bool leader, int bar, int count)
+{
+    if (leader)
+        for (int ty = known; ty <= ty_hi; ++ty) spin_wait_flag_geq(done + ty, need, err);
+    group_sync(bar, count);
+}
+
+// =========================== producers: buckets of tile i -> bucket tile [i & 1] ===========================
+// chain warps (stage B) and bucket warps (stage C) of one pass; tid = thread index inside the producer group
+template <typename PixT, int PT, int UPS, bool DEP>
+__device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int tid)
+{
     uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
     float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
     float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
-    unsigned long long *mbars = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
-    unsigned long long *mslice = mbars;
-
-    const int tid0 = threadIdx.x;
     const int th = p.tile_h, hh = th + 2;
     const int W = p.W, H = p.H;
     const int gx = (W + TW - 1) / TW;
-    const int ntiles = gx * ((p.row1 - p.row0 + th - 1) / th);
+    const int ntiles = pass_tiles(p);
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
 
-    if (p.numerics != 0 && tid0 < 256) sLut[tid0] = (tid0 < 128) ? p.lut_rsqrt14[tid0] : p.lut_rcp14[tid0 - 128];
+    // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
+    // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
+    // columns sx = 2t, 2t+1.  Split into load and store so that the global-memory latency hides behind stage B.
+    auto load_block = [&](int s, int t, int y0, int x0, unsigned &ab, unsigned &cd) {   // raw samples, two per register
+        const int j = (y0 - 7 + s) >> 1, i = (x0 - 7 + 2 * t) >> 1;
+        const int ya = min(max(j, 0), p.up_src_h - 1), yb = min(max(j + 1, 0), p.up_src_h - 1);
+        const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
+        const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
+        const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
+        ab = (unsigned)ra[xa] | ((unsigned)ra[xb] << 16);
+        cd = (unsigned)rb[xa] | ((unsigned)rb[xb] << 16);
+    };
+    auto store_block = [&](int s, int t, unsigned ab, unsigned cd) {
+        const float a = (float)(ab & 0xffffu), b = (float)(ab >> 16), c = (float)(cd & 0xffffu), d = (float)(cd >> 16);
+        const float t0 = ffma(3.0f, a, c), t1 = ffma(3.0f, b, d);     // row Y   : 3*row(j) + row(j+1)
+        const float u0 = ffma(3.0f, c, a), u1 = ffma(3.0f, d, b);     // row Y+1 : row(j) + 3*row(j+1)
+        float *r0 = sRing + (s & (RING - 1)) * SP + 2 * t, *r1 = sRing + ((s + 1) & (RING - 1)) * SP + 2 * t;
+        r0[0] = floorf(fmul(fadd(ffma(3.0f, t0, t1), 8.0f), 0.0625f));   // col X   : 3*col(i) + col(i+1)
+        r0[1] = floorf(fmul(fadd(ffma(3.0f, t1, t0), 8.0f), 0.0625f));   // col X+1 : col(i) + 3*col(i+1)
+        r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
+        r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
+    };
+    const bool chain_warp = tid >= NBT;                                  // sub-role: stage B (column chains) or stage C (buckets)
+    const int lt = tid & (NBT - 1);
+    // The two producer roles run as one pipeline over all chunks of all tiles of this CTA: the chain warps are one chunk
+    // ahead of the bucket warps (double-buffered chains, buffer = running chunk number & 1, one BAR_PROD per chunk), also
+    // across tile (and pass) boundaries, where the chain warps refill the ring while the bucket warps finish the previous tile.
+    bool input_complete = false;
+    int dep_known = 0;                                                   // DEP: tile rows [0, dep_known) of the previous pass seen complete
+    for (int tile = tile0; tile < ntiles; tile += gridDim.x, ++cy.iter) {
+        const int buf = cy.iter & 1;
+        unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
+        unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
+        const int ty = tile / gx, tx = tile - ty * gx;
+        const int x0 = tx * TW, y0 = p.row0 + ty * th;
+        const int rl = lt / QW, q = lt - rl * QW;            // this thread's row of a chunk and chain column / pixel column
+        const unsigned gk = cy.gk;
+        // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
+        // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
+        auto stage_B = [&](int kb) {
+            const int s0 = RBP * kb + rl;                            // S row above the first gradient row
+            f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
+            float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
+            const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
+            float vcur = row[1];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+                const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
+                const float vnext = nrow[1];
+                const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
+                const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
+                const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm) {
+                    const f32x2 w2 = pack2(p.gw[i][2 * mm], p.gw[i][2 * mm + 1]);
+                    const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
+                    acc[mm][0] = fma2(px, gx2, acc[mm][0]);
+                    acc[mm][1] = fma2(px, gy2, acc[mm][1]);
+                    acc[mm][2] = fma2(py, gy2, acc[mm][2]);
+                }
+                vprev = vcur; vcur = vnext; row = nrow;
+            }
+            float *qd = sQ + ((gk + kb) & 1u) * QCHUNK + (rl * 18) * QW + q;
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float lo, hi;
+                    unpack2(acc[mm][k], lo, hi);
+                    qd[(2 * mm * 3 + k) * QW] = lo;
+                    qd[((2 * mm + 1) * 3 + k) * QW] = hi;
+                }
+        };
+        // ---- C: bucket of chunk kc, one pixel per thread <- sQ[kc & 1].  The 16-wide hash runs unconditionally (garbage in,
+        // nothing stored, for threads without a hashed pixel); only the row-tail columns take the 8-wide branch.
+        auto stage_C = [&](int kc) {
+            const int h = RBP * kc + rl;
+            const int j = min(q, HW - 1);
+            const int r = y0 - 1 + h, c = x0 - 1 + j;
+            float g[3];
+            const float *qs = sQ + ((gk + kc) & 1u) * QCHUNK + (rl * 18) * QW + j;
+#pragma unroll
+            for (int k3 = 0; k3 < 3; ++k3) {
+                float lane[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    const int m = k < 6 ? k : 10 - k;
+                    lane[k] = qs[(m * 3 + k3) * QW + k];
+                }
+                g[k3] = tree_sum(lane);
+            }
+            const bool hashed = r >= 6 && r < H - 6 && c >= 6 && c < p.c_end;
+            int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
+            if (hashed && c >= p.tail_start) {
+                const int h8 = hash_bucket<false>(hc, g[0], g[1], g[2]);
+                if (c < p.ov_end && hv != h8) hv2 = hv;         // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
+                hv = h8;
+            }
+            if (!hashed) hv = 255;
+            if (q < HW && h < hh) {
+                if (p.hash_out && hashed && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
+                sHash[h * HP + j] = (unsigned char)hv;
+                if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
+            }
+        };
+        const int nchunks = hh / RBP;
+        if (chain_warp) {
+            // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Both reader groups
+            // look for themselves (the filter warps' stage A): neither is ordered behind the other's wait.
+            if (!DEP && p.in_ready && !input_complete) {
+                int in_lo, in_last;
+                tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
+                if (in_last >= p.in_split_row) {
+                    wait_split_input(p.in_ready, p.in_seq, p.err_flag, lt == 0, BAR_CHAIN, NBT);
+                    input_complete = true;
+                }
+            }
+            if (DEP) {                                                   // chained pass: the previous pass's rows this tile reads
+                int in_lo, in_hi;
+                tile_input_rows<UPS>(p, y0, th, in_lo, in_hi);
+                const int ty_hi = min(p.dep_ny - 1, (min(in_hi, p.dep_row1 - 1) - p.dep_row0) / p.dep_th);
+                if (ty_hi >= dep_known) {
+                    wait_rows_done(p.dep_done, (unsigned)p.dep_gx, ty_hi, dep_known, p.err_flag, lt == 0, BAR_CHAIN, NBT);
+                    dep_known = ty_hi + 1;
+                }
+            }
+            // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1)
+            // reads rows 2k .. 2k+13.  Rows 0 .. 13 up front (the previous tile's last B is done: BAR_PROD), every chunk then
+            // fetches the two rows of the NEXT chunk into the slots of rows 2k-2, 2k-1.
+            if (UPS == 1) {
+                for (int idx = lt; idx < ((RING - RBP) / 2) * (SW / 2); idx += NBT) {
+                    const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
+                    unsigned ab, cd;
+                    load_block(2 * sp2, t, y0, x0, ab, cd);
+                    store_block(2 * sp2, t, ab, cd);
+                }
+            } else {
+                for (int idx = lt; idx < (RING - RBP) * SW; idx += NBT) {
+                    const int s = idx / SW, sx = idx - s * SW;
+                    sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                }
+            }
+            group_sync(BAR_CHAIN, NBT);
+            for (int k = 0; k < nchunks; ++k) {
+                const bool more = k + 1 < nchunks;
+                unsigned pab = 0u, pcd = 0u;
+                if (UPS == 1 && more && lt < SW / 2) load_block(RBP * k + RING - RBP, lt, y0, x0, pab, pcd);
+                stage_B(k);
+                if (more) {
+                    if (UPS == 1) {
+                        if (lt < SW / 2) store_block(RBP * k + RING - RBP, lt, pab, pcd);
+                    } else {
+                        for (int idx = lt; idx < RBP * SW; idx += NBT) {
+                            const int s = RBP * k + RING - RBP + idx / SW, sx = idx % SW;
+                            sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                        }
+                    }
+                }
+                group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
+            }
+        } else {
+            if (cy.iter >= 2) group_sync(BAR_EMPTY + buf, NBT + NCT);    // the filter warps are done with this bucket tile (two tiles ago)
+            for (int k = 0; k < nchunks; ++k) {
+                group_sync(BAR_PROD, NPT);                               // B(k) is complete
+                stage_C(k);
+            }
+            named_arrive(BAR_FULL + buf, NBT + NCT);                     // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
+        }
+        cy.gk += (unsigned)nchunks;
+    }
+}
+
+// =========================== filter warps: S tile, filter, blend and store of tile i ===========================
+// F16: opt-in fp16 filter stage (RAISR_NUMERICS_FP16_FILTER): the filter slice holds half-precision coefficients (half the
+// bytes per slice and per row), patch values are converted to half2 and the 16 chains run as HMUL2/HFMA2; the 16 chain sums are
+// then added in fp32 with the same tree.  Buckets are untouched (the hash stays fp32); Y is NOT bit-identical in this mode.
+template <typename PixT, int PT, int UPS, bool DEP, bool F16>
+__device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int ct)
+{
+    float *sS = reinterpret_cast<float *>(smem_raw + POFF_S);
+    float *sHR = reinterpret_cast<float *>(smem_raw + POFF_HR);
+    float *sF = reinterpret_cast<float *>(smem_raw + POFF_F);
+    unsigned long long *mslice = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
+    const int th = p.tile_h, hh = th + 2;
+    const int W = p.W, H = p.H;
+    const int gx = (W + TW - 1) / TW;
+    const int ntiles = pass_tiles(p);
+
+    const int lane = ct & 31, cwarp = __shfl_sync(0xffffffffu, ct >> 5, 0);   // warp-uniform for the compiler too
+    const int g = lane >> 3, q = lane & 7;
+    constexpr int JS = (PT == 4) ? 2 : 1;
+    constexpr int U = 4;
+    constexpr int NCOLS = (HW + JS - 1) / JS;
+    constexpr int NBLK = (NCOLS + 4 * U - 1) / (4 * U);
+    constexpr int ULAST = (NCOLS - 4 * U * (NBLK - 1) + 3) / 4;
+    constexpr int ROWB = F16 ? 256 : 512;                                 // bytes of one filter row in the slice
+    constexpr int ROWSH = F16 ? 8 : 9;
+    int off[8][2];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 16 * m + 2 * q + e;
+            off[m][e] = (k < 121) ? (k / 11) * SP + (k % 11) : 0;
+        }
+    const float flo = (float)p.lo, fhi = (float)p.hi;
+    const int slice_bytes = p.nbuckets * ROWB;
+    // per-lane constant parts of the fast block's shared addresses (bytes): pixel group g, lane q of the group
+    unsigned poff[8][2];                                              // patch tap (m, e) of the group's pixel in block column 0
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            poff[m][e] = smem_u32(sS) + 4u * (unsigned)(off[m][e] + SP + 1 + g * JS);
+            asm volatile("" : "+r"(poff[m][e]));                      // keep the 16 addresses in registers (no rematerialisation per block)
+        }
+    const unsigned fbase = smem_u32(sF) + (unsigned)(ROWB / 32) * (unsigned)q;   // this lane's 16 (fp16: 8) bytes of every filter step
+    const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
+    // ---- chroma planes: plain cheap upscale (Raisr.cpp:1373-1388), 4 pixels per thread.  This CTA's share of the planes is
+    // cut into up to three slices, one per tile from the third tile on (the planes' H2D copies have landed by then), done while the filter warps would otherwise wait for
+    // the bucket tile: no launch of its own, and finished early enough for the host to copy the planes out while the luma runs on.
+    const int cta_tiles = (ntiles > tile0) ? (ntiles - tile0 + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nslices = min(3, max(1, cta_tiles - 2));                   // early in the frame: the host may copy the planes out while the luma runs on
+    int slices_done = 0;
+    auto chroma_slice = [&](int sl) {                                 // by value: never take the address of the kernel parameter block
+        ChromaParams cp;
+        cp.chroma_n = p.chroma_n;
+        for (int i = 0; i < 2; ++i) { cp.in[i] = p.chroma[i].in; cp.in_pitch[i] = p.chroma[i].in_pitch; cp.out[i] = p.chroma[i].out; cp.out_pitch[i] = p.chroma[i].out_pitch; }
+        cp.c_in_w = p.c_in_w; cp.c_in_h = p.c_in_h; cp.c_W = p.c_W; cp.c_H = p.c_H;
+        cp.c_xmap = p.c_xmap; cp.c_xw = p.c_xw; cp.c_ymap = p.c_ymap; cp.c_yw = p.c_yw; cp.c_denx = p.c_denx; cp.c_deny = p.c_deny;
+        cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done; cp.err_flag = p.err_flag;
+        chroma_slice_fn<PixT>(cp, sl, nslices, ct);
+    };
+    int resident_type = -1;                                           // pixel type whose filter slice (of THIS pass's table) is in shared memory
+    int local_iter = 0;
+    bool input_complete = false;
+    for (int tile = tile0; tile < ntiles; tile += gridDim.x, ++cy.iter, ++local_iter) {
+        const int buf = cy.iter & 1;
+        const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
+        const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
+        const int ty = tile / gx, tx = tile - ty * gx;
+        const int x0 = tx * TW, y0 = p.row0 + ty * th;
+        // Stage A reads the same input rows as the chain warps' ring of this tile, and nothing else orders it behind THEIR waits
+        // (split H2D flag; chained pass: rows of the previous pass).  Where such a wait can be pending the filter warps take this
+        // tile's FULL barrier BEFORE stage A instead of after it: the buckets of the tile exist only once the chain warps have
+        // seen the flag (leader's ld.acquire -> BAR_CHAIN -> BAR_PROD -> BAR_FULL: causality is cumulative).  The producers run a
+        // tile ahead, so the barrier has usually completed long before and nothing is lost.
+        bool full_taken = false;
+        if (DEP) {
+            group_sync(BAR_FULL + buf, NBT + NCT);
+            full_taken = true;
+        } else if (p.in_ready && !input_complete) {
+            int in_lo, in_last;
+            tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
+            if (in_last >= p.in_split_row) {
+                group_sync(BAR_FULL + buf, NBT + NCT);
+                full_taken = input_complete = true;
+            }
+        }
+
+        // ---- A: S tile (the HR tile is free until the HR := S copy below: low-res staging for the 2x path; the slice buffer
+        // keeps the previous tile's last filter slice) ----
+        if (UPS == 1) {
+            float *sL = sHR;
+            const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;
+            const int lrh = (th + 14) / 2 + 1;
+            for (int idx = ct; idx < lrh * LRW; idx += NCT) {
+                const int ly = idx / LRW, lx = idx - ly * LRW;
+                const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
+                sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
+            }
+            group_sync(BAR_CONS, NCT);
+            for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
+                const int bi = idx / (LRW - 1) + 1, bj = idx - (bi - 1) * (LRW - 1) + 1;
+                const float *l = sL + bi * LRP + bj;
+                const float a0 = l[-LRP - 1], a1 = l[-LRP], b0 = l[-1], b1 = l[0];
+                const float vo0 = ffma(3.0f, a0, b0), vo1 = ffma(3.0f, a1, b1);
+                const float ve0 = ffma(3.0f, b0, a0), ve1 = ffma(3.0f, b1, a1);
+                float *d = sS + (2 * bi - 2) * SP + 2 * bj - 2;
+                d[0] = floorf(fmul(fadd(ffma(3.0f, vo0, vo1), 8.0f), 0.0625f));
+                d[1] = floorf(fmul(fadd(ffma(3.0f, vo1, vo0), 8.0f), 0.0625f));
+                d[SP] = floorf(fmul(fadd(ffma(3.0f, ve0, ve1), 8.0f), 0.0625f));
+                d[SP + 1] = floorf(fmul(fadd(ffma(3.0f, ve1, ve0), 8.0f), 0.0625f));
+            }
+        } else {
+            for (int idx = ct; idx < (th + 14) * SW; idx += NCT) {
+                const int sy = idx / SW, sx = idx - sy * SW;
+                const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
+                float v = 0.0f;
+                if (Y >= 0 && Y < H && X >= 0 && X < W) v = load_S<PixT>(p, Y, X, UPS != 0);
+                sS[sy * SP + sx] = v;
+            }
+        }
+        group_sync(BAR_CONS, NCT);
+        // HR := S; the filter phase overwrites accepted pixels
+        for (int idx = ct; idx < hh * HW; idx += NCT) {
+            const int h = idx / HW, j = idx - h * HW;
+            sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
+        }
+        if (p.chroma_n > 0 && local_iter >= 2 && slices_done < nslices) chroma_slice(slices_done++);
+        group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
+        if (!full_taken) group_sync(BAR_FULL + buf, NBT + NCT);           // buckets of this tile are ready
+
+        // ---- D: 121-tap filter, one pixel type at a time ----
+        const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
+        // pixel types in alternating order (0..PT-1, then PT-1..0): the slice the previous tile ended with is still resident
+        for (int ti = 0; ti < PT; ++ti) {
+            const int t = (local_iter & 1) ? PT - 1 - ti : ti;
+            const bool load = t != resident_type;
+            if (load && ct == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(mslice, (unsigned)slice_bytes);
+                const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
+                const int piece = slice_bytes / 4;
+                for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mslice);
+            }
+            const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;
+            const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
+            const int nrows = (hh - hfirst + JS - 1) / JS;
+            if (load) {
+                mbar_wait(mslice, cy.nload & 1u);
+                ++cy.nload;
+                resident_type = t;
+            }
+            // One warp iteration = UU groups of 4 pixels of one tile row: addresses = per-lane constant + uniform + immediate,
+            // packed FMUL2/FFMA2 for the chain pair (2q, 2q+1), and the 16 -> 1 lane tree of the 4 pixel groups folded into 8 shuffles:
+            // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
+            // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
+            const unsigned hbase = smem_u32(sHash) + (unsigned)(g * JS);
+            const unsigned lastrow = (unsigned)p.nbuckets - 1u;
+            auto fast_block = [&](auto uu, const int h, const int jc0) {   // h, jc0 (block column 0) are warp-uniform
+                constexpr int UU = decltype(uu)::value;
+                const unsigned ub = 4u * (unsigned)(h * SP + jc0);
+                const unsigned hva = hbase + (unsigned)(h * HP + jc0);
+                unsigned hv[4], fa[4];
+                hv[0] = lds_u8<0>(hva); hv[1] = lds_u8<4 * JS>(hva);
+                hv[2] = (UU > 2) ? lds_u8<8 * JS>(hva) : 255u; hv[3] = (UU > 3) ? lds_u8<12 * JS>(hva) : 255u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fa[u] = fbase + (min(hv[u], lastrow) << ROWSH);   // 255 (not hashed): any row of the slice, result dropped
+                f32x2 acc[4];                                                 // fp32: (chain 2q, chain 2q+1);  F16: .x of the pair holds the half2
+                unsigned acch[4];
+                auto step = [&](auto nn) {
+                    constexpr int n = decltype(nn)::value;
+                    const unsigned q0 = poff[2 * n][0] + ub, q1 = poff[2 * n][1] + ub, q2 = poff[2 * n + 1][0] + ub, q3 = poff[2 * n + 1][1] + ub;
+                    auto one = [&](auto uc) {
+                        constexpr int u = decltype(uc)::value;
+                        if (u < UU) {
+                            if (F16) {
+                                unsigned f01, f23;                            // half2 coefficients of chunks 2n and 2n+1
+                                lds_b32x2<n * 64>(fa[u], f01, f23);
+                                const unsigned p01 = f2h2(lds_f32<16 * JS * u>(q0), lds_f32<16 * JS * u>(q1));
+                                const unsigned p23 = f2h2(lds_f32<16 * JS * u>(q2), lds_f32<16 * JS * u>(q3));
+                                acch[u] = (n == 0) ? hmul2(p01, f01) : hfma2(p01, f01, acch[u]);
+                                acch[u] = hfma2(p23, f23, acch[u]);
+                            } else {
+                                f32x2 fxy, fzw;
+                                lds_f32x2x2<n * 128>(fa[u], fxy, fzw);
+                                const f32x2 p01 = pack2(lds_f32<16 * JS * u>(q0), lds_f32<16 * JS * u>(q1));
+                                const f32x2 p23 = pack2(lds_f32<16 * JS * u>(q2), lds_f32<16 * JS * u>(q3));
+                                acc[u] = (n == 0) ? mul2(p01, fxy) : fma2(p01, fxy, acc[u]);
+                                acc[u] = fma2(p23, fzw, acc[u]);
+                            }
+                        }
+                    };
+                    one(std::integral_constant<int, 0>{}); one(std::integral_constant<int, 1>{});
+                    one(std::integral_constant<int, 2>{}); one(std::integral_constant<int, 3>{});
+                };
+                step(std::integral_constant<int, 0>{}); step(std::integral_constant<int, 1>{});
+                step(std::integral_constant<int, 2>{}); step(std::integral_constant<int, 3>{});
+                // t8: lanes q < 4 keep chain 2q and take chain 2q of lane q+4; lanes q >= 4 keep chain 2q+1 and take it from lane q-4
+                const bool hi4 = q >= 4, b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (u < UU) {
+                        float a0, a1;
+                        if (F16) h2f2(acch[u], a0, a1); else unpack2(acc[u], a0, a1);
+                        v[u] = fadd(hi4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi4 ? a0 : a1, 4, 8));
+                    } else v[u] = 0.0f;
+                }
+                // t4: lanes with q & 2 keep pixels 2,3 and send 0,1; the others keep 0,1 and send 2,3
+                const float w0 = fadd(b1 ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2, 8));
+                const float w1 = fadd(b1 ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2, 8));
+                // t2: lanes with q & 1 keep the odd pixel
+                const float x = fadd(b0 ? w1 : w0, __shfl_xor_sync(0xffffffffu, b0 ? w0 : w1, 1, 8));
+                const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));      // t2[0] + t2[1]: pixel u = q & 3
+                const unsigned hu = b1 ? (b0 ? hv[3] : hv[2]) : (b0 ? hv[1] : hv[0]);
+                if (q < 4 && hu != 255u && cur > flo && cur < fhi)              // strict range test, Raisr.cpp:1192-1196
+                    sts_f32(hroff + 4u * (unsigned)(h * HP + jc0), cur);
+            };
+            // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
+            // single pixel groups over all warps so that no warp waits a whole item at the barrier.  Items without a hashed
+            // pixel (rows outside [6, H-6), columns from c_end on) are skipped: HR stays S there.
+            const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
+            auto live = [&](int h, int jc0) {
+                const int r = y0 - 1 + h;
+                return r >= 6 && r < H - 6 && x0 - 1 + jc0 < p.c_end;
+            };
+            for (int it = cwarp; it < nfull; it += NCW) {
+                const int ri = it / NBLK, bi = it - ri * NBLK;
+                const int h = hfirst + ri * JS, jc0 = jfirst + bi * 4 * U * JS;
+                if (!live(h, jc0)) continue;
+                if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jc0);
+                else fast_block(std::integral_constant<int, ULAST>{}, h, jc0);
+            }
+            for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
+                const int it = nfull + rq / U, u = rq - (rq / U) * U;
+                const int ri = it / NBLK, bi = it - ri * NBLK;
+                const int h = hfirst + ri * JS, jc0 = jfirst + (bi * 4 * U + 4 * u) * JS;
+                if ((bi == NBLK - 1 && u >= ULAST) || !live(h, jc0)) continue;
+                fast_block(std::integral_constant<int, 1>{}, h, jc0);
+            }
+            // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
+            // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
+            if (has_ov && p.blending == 2) {
+                const int jlo = max(jfirst, p.tail_start - (x0 - 1)), jhi = min(HW, p.tail_start + OVW - (x0 - 1));
+                const int j0 = jlo + ((jlo - jfirst) % JS != 0 ? JS - (jlo - jfirst) % JS : 0);   // first column of this type in the overlap
+                const int ncol = (jhi > j0) ? (jhi - j0 + JS - 1) / JS : 0;
+                const int total = nrows * ncol;
+                for (int base = cwarp * 4; base < total; base += NCW * 4) {
+                    const int pi = min(base + g, total - 1);
+                    const int ri = pi / ncol, ci = pi - ri * ncol;
+                    const int h = hfirst + ri * JS, j = j0 + ci * JS;
+                    const int hv = sHash[h * HP + j];
+                    const int hv2 = sHash2[h * OVW + (x0 - 1 + j - p.tail_start)];
+                    const float *sp = sS + (h + 1) * SP + j + 1;
+                    const char *fb = reinterpret_cast<const char *>(sF);
+                    const float cur8 = F16 ? dot8_h(sp, fb + (hv == 255 ? 0 : hv) * ROWB, off, q) : dot8(sp, sF + (hv == 255 ? 0 : hv) * 128, off, q);
+                    const float cur16 = F16 ? dot8_h(sp, fb + (hv2 == 255 ? 0 : hv2) * ROWB, off, q) : dot8(sp, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
+                    const bool ok8 = cur8 > flo && cur8 < fhi;
+                    if (q == 0 && base + g < total && hv != 255 && hv2 != 255 && !ok8 && cur16 > flo && cur16 < fhi) sHR[h * HP + j] = cur16;
+                }
+            }
+            group_sync(BAR_CONS, NCT);
+        }
+        // ---- E: blend + store ----
+        stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
+        group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
+        if (cy.iter + 2 < cy.total_iters) named_arrive(BAR_EMPTY + buf, NBT + NCT);   // bucket tile may be refilled (two tiles on, possibly in the next pass)
+        if (ct == 0 && (p.band_done || p.rows_done)) {
+            __threadfence();                                              // the tile's stores (ordered before by the barrier) -> device scope
+            if (p.band_done && !(p.out_tail && y0 >= p.tail_row0)) atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
+            if (p.rows_done) atomicAdd(p.rows_done + ty, 1u);             // chained launch: the next pass waits for whole tile rows
+        }
+    }
+    if (p.chroma_n > 0)
+        while (slices_done < nslices) chroma_slice(slices_done++);       // CTAs with fewer than three tiles
+}
+
+// UPSA / UPSB: upscale flavour of the first / second pass of the launch (0 = none, 1 = exact 2x, 2 = axis maps); UPSB = -1: one
+// pass.  With two passes (pb.dep_done set by the host, cooperative launch: all CTAs resident) the second pass reads the plane
+// the first one writes; tile rows are handed over through pa.rows_done / pb.dep_done.
+template <typename PixT, int PT, int UPSA, int UPSB, bool F16>
+__global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_constant__ PassParams pa, const __grid_constant__ PassParams pb)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
+    unsigned long long *mslice = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
+    const int tid0 = threadIdx.x;
+
+    if (pa.numerics != 0 && tid0 < 256) sLut[tid0] = (tid0 < 128) ? pa.lut_rsqrt14[tid0] : pa.lut_rcp14[tid0 - 128];
     for (int i = tid0; i < 2 * PHH * (HP - HW); i += NTP)                 // pad columns of both bucket tiles: "not hashed"
         smem_raw[POFF_HASH + (size_t)(i / (HP - HW)) * HP + HW + i % (HP - HW)] = 255;
     if (tid0 == 0) {
@@ -265,424 +814,27 @@ __global__ void __launch_bounds__(NTP, 1) raisr_pass_pipe_kernel(const PassParam
     }
     __syncthreads();
 
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
+    // this CTA's share of the launch: tiles blockIdx.x, +gridDim.x, ... of the combined sequence (pass A, then pass B)
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int tA = pass_tiles(pa);
+    const int tB = (UPSB >= 0) ? pass_tiles(pb) : 0;
+    const int nA = (tA > b) ? (tA - b + G - 1) / G : 0;
+    const int tileB0 = b + nA * G - tA;                                   // first tile of pass B for this CTA (>= 0)
+    const int nB = (tB > tileB0) ? (tB - tileB0 + G - 1) / G : 0;
+    PipeCarry cy{0, nA + nB, 0u, 0u};
 
     // warps [0, NCW) are the filter warps, warps [NCW, NCW + NPW) the producers (bucket warps, then chain warps)
-    const bool is_prod = tid0 >= NCT;
-    const int tid = tid0 - NCT, ct = tid0;
-    if (is_prod) {
-        // =========================== producer: buckets of tile i -> bucket tile [i & 1] ===========================
+    if (tid0 >= NCT) {
+        const int tid = tid0 - NCT;
         // hand registers to the filter warpgroups; the chain warps (18 accumulators) need fewer than the hash
         if (tid >= NBT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BUCKET_REGS));
-        // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
-        // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
-        // columns sx = 2t, 2t+1.  Split into load and store so that the global-memory latency hides behind stage B.
-        auto load_block = [&](int s, int t, int y0, int x0, unsigned &ab, unsigned &cd) {   // raw samples, two per register
-            const int j = (y0 - 7 + s) >> 1, i = (x0 - 7 + 2 * t) >> 1;
-            const int ya = min(max(j, 0), p.up_src_h - 1), yb = min(max(j + 1, 0), p.up_src_h - 1);
-            const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
-            const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
-            const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
-            ab = (unsigned)ra[xa] | ((unsigned)ra[xb] << 16);
-            cd = (unsigned)rb[xa] | ((unsigned)rb[xb] << 16);
-        };
-        auto store_block = [&](int s, int t, unsigned ab, unsigned cd) {
-            const float a = (float)(ab & 0xffffu), b = (float)(ab >> 16), c = (float)(cd & 0xffffu), d = (float)(cd >> 16);
-            const float t0 = ffma(3.0f, a, c), t1 = ffma(3.0f, b, d);     // row Y   : 3*row(j) + row(j+1)
-            const float u0 = ffma(3.0f, c, a), u1 = ffma(3.0f, d, b);     // row Y+1 : row(j) + 3*row(j+1)
-            float *r0 = sRing + (s & (RING - 1)) * SP + 2 * t, *r1 = sRing + ((s + 1) & (RING - 1)) * SP + 2 * t;
-            r0[0] = floorf(fmul(fadd(ffma(3.0f, t0, t1), 8.0f), 0.0625f));   // col X   : 3*col(i) + col(i+1)
-            r0[1] = floorf(fmul(fadd(ffma(3.0f, t1, t0), 8.0f), 0.0625f));   // col X+1 : col(i) + 3*col(i+1)
-            r1[0] = floorf(fmul(fadd(ffma(3.0f, u0, u1), 8.0f), 0.0625f));
-            r1[1] = floorf(fmul(fadd(ffma(3.0f, u1, u0), 8.0f), 0.0625f));
-        };
-        const bool chain_warp = tid >= NBT;                                  // sub-role: stage B (column chains) or stage C (buckets)
-        const int lt = tid & (NBT - 1);
-        // The two producer roles run as one pipeline over all chunks of all tiles of this CTA: the chain warps are one chunk
-        // ahead of the bucket warps (double-buffered chains, buffer = running chunk number & 1, one BAR_PROD per chunk), also
-        // across tile boundaries, where the chain warps refill the ring while the bucket warps finish the previous tile.
-        int iter = 0;
-        unsigned gk = 0;                                                     // running chunk number
-        bool input_complete = false;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-            const int buf = iter & 1;
-            unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
-            unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
-            const int ty = tile / gx, tx = tile - ty * gx;
-            const int x0 = tx * TW, y0 = p.row0 + ty * th;
-            const int rl = lt / QW, q = lt - rl * QW;            // this thread's row of a chunk and chain column / pixel column
-            // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
-            // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
-            auto stage_B = [&](int kb) {
-                const int s0 = RBP * kb + rl;                            // S row above the first gradient row
-                f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
-                float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
-                const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
-                float vcur = row[1];
-#pragma unroll
-                for (int i = 0; i < 11; ++i) {
-                    const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
-                    const float vnext = nrow[1];
-                    const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
-                    const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
-                    const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
-#pragma unroll
-                    for (int mm = 0; mm < 3; ++mm) {
-                        const f32x2 w2 = pack2(p.gw[i][2 * mm], p.gw[i][2 * mm + 1]);
-                        const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
-                        acc[mm][0] = fma2(px, gx2, acc[mm][0]);
-                        acc[mm][1] = fma2(px, gy2, acc[mm][1]);
-                        acc[mm][2] = fma2(py, gy2, acc[mm][2]);
-                    }
-                    vprev = vcur; vcur = vnext; row = nrow;
-                }
-                float *qd = sQ + ((gk + kb) & 1u) * QCHUNK + (rl * 18) * QW + q;
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        float lo, hi;
-                        unpack2(acc[mm][k], lo, hi);
-                        qd[(2 * mm * 3 + k) * QW] = lo;
-                        qd[((2 * mm + 1) * 3 + k) * QW] = hi;
-                    }
-            };
-            // ---- C: bucket of chunk kc, one pixel per thread <- sQ[kc & 1].  The 16-wide hash runs unconditionally (garbage in,
-            // nothing stored, for threads without a hashed pixel); only the row-tail columns take the 8-wide branch.
-            auto stage_C = [&](int kc) {
-                const int h = RBP * kc + rl;
-                const int j = min(q, HW - 1);
-                const int r = y0 - 1 + h, c = x0 - 1 + j;
-                float g[3];
-                const float *qs = sQ + ((gk + kc) & 1u) * QCHUNK + (rl * 18) * QW + j;
-#pragma unroll
-                for (int k3 = 0; k3 < 3; ++k3) {
-                    float lane[11];
-#pragma unroll
-                    for (int k = 0; k < 11; ++k) {
-                        const int m = k < 6 ? k : 10 - k;
-                        lane[k] = qs[(m * 3 + k3) * QW + k];
-                    }
-                    g[k3] = tree_sum(lane);
-                }
-                const bool hashed = r >= 6 && r < H - 6 && c >= 6 && c < p.c_end;
-                int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
-                if (hashed && c >= p.tail_start) {
-                    const int h8 = hash_bucket<false>(hc, g[0], g[1], g[2]);
-                    if (c < p.ov_end && hv != h8) hv2 = hv;         // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
-                    hv = h8;
-                }
-                if (!hashed) hv = 255;
-                if (q < HW && h < hh) {
-                    if (p.hash_out && hashed && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
-                    sHash[h * HP + j] = (unsigned char)hv;
-                    if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
-                }
-            };
-            const int nchunks = hh / RBP;
-            if (chain_warp) {
-                // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Both reader groups
-                // look for themselves (the filter warps' stage A below): neither is ordered behind the other's wait.
-                if (p.in_ready && !input_complete) {
-                    const int ylast = min(H - 1, y0 + th + 6);
-                    const int in_last = (UPS == 0) ? ylast : (UPS == 1) ? (ylast >> 1) + 1 : (__ldg(p.ymap + ylast) >> 1) + 1;
-                    if (in_last >= p.in_split_row) {
-                        wait_split_input(p.in_ready, p.in_seq, p.err_flag, lt == 0, BAR_CHAIN, NBT);
-                        input_complete = true;
-                    }
-                }
-                // S ring: tile-local S row s (frame row y0-7+s) lives in ring row s & (RING-1); chunk k (filtered rows 2k, 2k+1)
-                // reads rows 2k .. 2k+13.  Rows 0 .. 13 up front (the previous tile's last B is done: BAR_PROD), every chunk then
-                // fetches the two rows of the NEXT chunk into the slots of rows 2k-2, 2k-1.
-                if (UPS == 1) {
-                    for (int idx = lt; idx < ((RING - RBP) / 2) * (SW / 2); idx += NBT) {
-                        const int sp2 = idx / (SW / 2), t = idx - sp2 * (SW / 2);
-                        unsigned ab, cd;
-                        load_block(2 * sp2, t, y0, x0, ab, cd);
-                        store_block(2 * sp2, t, ab, cd);
-                    }
-                } else {
-                    for (int idx = lt; idx < (RING - RBP) * SW; idx += NBT) {
-                        const int s = idx / SW, sx = idx - s * SW;
-                        sRing[s * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
-                    }
-                }
-                group_sync(BAR_CHAIN, NBT);
-                for (int k = 0; k < nchunks; ++k) {
-                    const bool more = k + 1 < nchunks;
-                    unsigned pab = 0u, pcd = 0u;
-                    if (UPS == 1 && more && lt < SW / 2) load_block(RBP * k + RING - RBP, lt, y0, x0, pab, pcd);
-                    stage_B(k);
-                    if (more) {
-                        if (UPS == 1) {
-                            if (lt < SW / 2) store_block(RBP * k + RING - RBP, lt, pab, pcd);
-                        } else {
-                            for (int idx = lt; idx < RBP * SW; idx += NBT) {
-                                const int s = RBP * k + RING - RBP + idx / SW, sx = idx % SW;
-                                sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
-                            }
-                        }
-                    }
-                    group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
-                }
-            } else {
-                if (iter >= 2) group_sync(BAR_EMPTY + buf, NBT + NCT);       // the filter warps are done with this bucket tile (tile i-2)
-                for (int k = 0; k < nchunks; ++k) {
-                    group_sync(BAR_PROD, NPT);                               // B(k) is complete
-                    stage_C(k);
-                }
-                named_arrive(BAR_FULL + buf, NBT + NCT);                     // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
-            }
-            gk += (unsigned)nchunks;
-        }
+        pipe_producer_pass<PixT, PT, UPSA, false>(pa, smem_raw, b, cy, tid);
+        if constexpr (UPSB >= 0) pipe_producer_pass<PixT, PT, UPSB, true>(pb, smem_raw, tileB0, cy, tid);
     } else {
-        // =========================== consumer: filter + blend of tile i ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-        const int lane = ct & 31, cwarp = __shfl_sync(0xffffffffu, ct >> 5, 0);   // warp-uniform for the compiler too
-        const int g = lane >> 3, q = lane & 7;
-        constexpr int JS = (PT == 4) ? 2 : 1;
-        constexpr int U = 4;
-        constexpr int NCOLS = (HW + JS - 1) / JS;
-        constexpr int NBLK = (NCOLS + 4 * U - 1) / (4 * U);
-        constexpr int ULAST = (NCOLS - 4 * U * (NBLK - 1) + 3) / 4;
-        int off[8][2];
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int k = 16 * m + 2 * q + e;
-                off[m][e] = (k < 121) ? (k / 11) * SP + (k % 11) : 0;
-            }
-        const float flo = (float)p.lo, fhi = (float)p.hi;
-        const int slice_bytes = p.nbuckets * 128 * (int)sizeof(float);
-        // per-lane constant parts of the fast block's shared addresses (bytes): pixel group g, lane q of the group
-        unsigned poff[8][2];                                              // patch tap (m, e) of the group's pixel in block column 0
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                poff[m][e] = smem_u32(sS) + 4u * (unsigned)(off[m][e] + SP + 1 + g * JS);
-                asm volatile("" : "+r"(poff[m][e]));                      // keep the 16 addresses in registers (no rematerialisation per block)
-            }
-        const unsigned fbase = smem_u32(sF) + 16u * (unsigned)q;          // this lane's 16 bytes of every 128-byte filter step
-        const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
-        // ---- chroma planes: plain cheap upscale (Raisr.cpp:1373-1388), 4 pixels per thread.  This CTA's share of the planes is
-        // cut into up to three slices, one per tile from the third tile on (the planes' H2D copies have landed by then), done while the filter warps would otherwise wait for
-        // the bucket tile: no launch of its own, and finished early enough for the host to copy the planes out under the kernel.
-        const int cta_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-        const int nslices = min(3, max(1, cta_tiles - 2));                   // early in the frame: the host may copy the planes out while the luma runs on
-        int slices_done = 0;
-        auto chroma_slice = [&](int sl) {                                 // by value: never take the address of the kernel parameter block
-            ChromaParams cp;
-            cp.chroma_n = p.chroma_n;
-            for (int i = 0; i < 2; ++i) { cp.in[i] = p.chroma[i].in; cp.in_pitch[i] = p.chroma[i].in_pitch; cp.out[i] = p.chroma[i].out; cp.out_pitch[i] = p.chroma[i].out_pitch; }
-            cp.c_in_w = p.c_in_w; cp.c_in_h = p.c_in_h; cp.c_W = p.c_W; cp.c_H = p.c_H;
-            cp.c_xmap = p.c_xmap; cp.c_xw = p.c_xw; cp.c_ymap = p.c_ymap; cp.c_yw = p.c_yw; cp.c_denx = p.c_denx; cp.c_deny = p.c_deny;
-            cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done; cp.err_flag = p.err_flag;
-            chroma_slice_fn<PixT>(cp, sl, nslices, ct);
-        };
-        unsigned nload = 0;
-        int resident_type = -1;                                           // pixel type whose filter slice is in shared memory
-        int iter = 0;
-        bool input_complete = false;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-            const int buf = iter & 1;
-            const unsigned char *sHash = smem_raw + POFF_HASH + (size_t)buf * PHH * HP;
-            const unsigned char *sHash2 = smem_raw + POFF_HASH2 + (size_t)buf * PHH * OVW;
-            const int ty = tile / gx, tx = tile - ty * gx;
-            const int x0 = tx * TW, y0 = p.row0 + ty * th;
-            // split H2D (see the chain warps): stage A reads the same input rows as the chain warps' ring of this tile, and nothing
-            // else orders it behind their flag wait.  For the first tile that reaches into the flagged rows the filter warps
-            // therefore take this tile's FULL barrier BEFORE stage A instead of after it: the buckets of the tile exist only once
-            // the chain warps have seen the flag (leader's ld.acquire -> BAR_CHAIN -> BAR_PROD -> BAR_FULL, causality is cumulative).
-            bool full_taken = false;
-            if (p.in_ready && !input_complete) {
-                const int ylast = min(H - 1, y0 + th + 6);
-                const int in_last = (UPS == 0) ? ylast : (UPS == 1) ? (ylast >> 1) + 1 : (__ldg(p.ymap + ylast) >> 1) + 1;
-                if (in_last >= p.in_split_row) {
-                    group_sync(BAR_FULL + buf, NBT + NCT);
-                    full_taken = input_complete = true;
-                }
-            }
-
-            // ---- A: S tile (the HR tile is free until the HR := S copy below: low-res staging for the 2x path; the slice buffer
-            // keeps the previous tile's last filter slice) ----
-            if (UPS == 1) {
-                float *sL = sHR;
-                const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;
-                const int lrh = (th + 14) / 2 + 1;
-                for (int idx = ct; idx < lrh * LRW; idx += NCT) {
-                    const int ly = idx / LRW, lx = idx - ly * LRW;
-                    const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
-                    sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
-                }
-                group_sync(BAR_CONS, NCT);
-                for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
-                    const int bi = idx / (LRW - 1) + 1, bj = idx - (bi - 1) * (LRW - 1) + 1;
-                    const float *l = sL + bi * LRP + bj;
-                    const float a0 = l[-LRP - 1], a1 = l[-LRP], b0 = l[-1], b1 = l[0];
-                    const float vo0 = ffma(3.0f, a0, b0), vo1 = ffma(3.0f, a1, b1);
-                    const float ve0 = ffma(3.0f, b0, a0), ve1 = ffma(3.0f, b1, a1);
-                    float *d = sS + (2 * bi - 2) * SP + 2 * bj - 2;
-                    d[0] = floorf(fmul(fadd(ffma(3.0f, vo0, vo1), 8.0f), 0.0625f));
-                    d[1] = floorf(fmul(fadd(ffma(3.0f, vo1, vo0), 8.0f), 0.0625f));
-                    d[SP] = floorf(fmul(fadd(ffma(3.0f, ve0, ve1), 8.0f), 0.0625f));
-                    d[SP + 1] = floorf(fmul(fadd(ffma(3.0f, ve1, ve0), 8.0f), 0.0625f));
-                }
-            } else {
-                for (int idx = ct; idx < (th + 14) * SW; idx += NCT) {
-                    const int sy = idx / SW, sx = idx - sy * SW;
-                    const int Y = y0 - 7 + sy, X = x0 - 7 + sx;
-                    float v = 0.0f;
-                    if (Y >= 0 && Y < H && X >= 0 && X < W) v = load_S<PixT>(p, Y, X, UPS != 0);
-                    sS[sy * SP + sx] = v;
-                }
-            }
-            group_sync(BAR_CONS, NCT);
-            // HR := S; the filter phase overwrites accepted pixels
-            for (int idx = ct; idx < hh * HW; idx += NCT) {
-                const int h = idx / HW, j = idx - h * HW;
-                sHR[h * HP + j] = sS[(h + 6) * SP + j + 6];
-            }
-            if (p.chroma_n > 0 && iter >= 2 && slices_done < nslices) chroma_slice(slices_done++);
-            group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
-            if (!full_taken) group_sync(BAR_FULL + buf, NBT + NCT);           // buckets of this tile are ready
-
-            // ---- D: 121-tap filter, one pixel type at a time ----
-            const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
-            // pixel types in alternating order (0..PT-1, then PT-1..0): the slice the previous tile ended with is still resident
-            for (int ti = 0; ti < PT; ++ti) {
-                const int t = (iter & 1) ? PT - 1 - ti : ti;
-                const bool load = t != resident_type;
-                if (load && ct == 0) {
-                    fence_proxy_async();
-                    mbar_expect_tx(mslice, (unsigned)slice_bytes);
-                    const char *src = reinterpret_cast<const char *>(p.filters) + (size_t)t * slice_bytes;
-                    const int piece = slice_bytes / 4;
-                    for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char *>(sF) + i * piece, src + i * piece, (unsigned)piece, mslice);
-                }
-                const int jfirst = (PT == 4) ? ((((x0 - 1 - 5) & 1) == (t & 1)) ? 0 : 1) : 0;
-                const int hfirst = (PT == 4) ? ((((y0 - 1 - 5) & 1) == (t >> 1)) ? 0 : 1) : 0;
-                const int nrows = (hh - hfirst + JS - 1) / JS;
-                if (load) {
-                    mbar_wait(mslice, nload & 1u);
-                    ++nload;
-                    resident_type = t;
-                }
-                // One warp iteration = UU groups of 4 pixels of one tile row: addresses = per-lane constant + uniform + immediate,
-                // packed FMUL2/FFMA2 for the chain pair (2q, 2q+1), and the 16 -> 1 lane tree of the 4 pixel groups folded into 8 shuffles:
-                // after the first exchange (t8) every lane keeps half of the pixels it holds and sends the other half, so that the
-                // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
-                const unsigned hbase = smem_u32(sHash) + (unsigned)(g * JS);
-                const unsigned lastrow = (unsigned)p.nbuckets - 1u;
-                auto fast_block = [&](auto uu, const int h, const int jc0) {   // h, jc0 (block column 0) are warp-uniform
-                    constexpr int UU = decltype(uu)::value;
-                    const unsigned ub = 4u * (unsigned)(h * SP + jc0);
-                    const unsigned hva = hbase + (unsigned)(h * HP + jc0);
-                    unsigned hv[4], fa[4];
-                    hv[0] = lds_u8<0>(hva); hv[1] = lds_u8<4 * JS>(hva);
-                    hv[2] = (UU > 2) ? lds_u8<8 * JS>(hva) : 255u; hv[3] = (UU > 3) ? lds_u8<12 * JS>(hva) : 255u;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) fa[u] = fbase + (min(hv[u], lastrow) << 9);   // 255 (not hashed): any row of the slice, result dropped
-                    f32x2 acc[4];
-                    auto step = [&](auto nn) {
-                        constexpr int n = decltype(nn)::value;
-                        const unsigned q0 = poff[2 * n][0] + ub, q1 = poff[2 * n][1] + ub, q2 = poff[2 * n + 1][0] + ub, q3 = poff[2 * n + 1][1] + ub;
-                        auto one = [&](auto uc) {
-                            constexpr int u = decltype(uc)::value;
-                            if (u < UU) {
-                                f32x2 fxy, fzw;
-                                lds_f32x2x2<n * 128>(fa[u], fxy, fzw);
-                                const f32x2 p01 = pack2(lds_f32<16 * JS * u>(q0), lds_f32<16 * JS * u>(q1));
-                                const f32x2 p23 = pack2(lds_f32<16 * JS * u>(q2), lds_f32<16 * JS * u>(q3));
-                                acc[u] = (n == 0) ? mul2(p01, fxy) : fma2(p01, fxy, acc[u]);
-                                acc[u] = fma2(p23, fzw, acc[u]);
-                            }
-                        };
-                        one(std::integral_constant<int, 0>{}); one(std::integral_constant<int, 1>{});
-                        one(std::integral_constant<int, 2>{}); one(std::integral_constant<int, 3>{});
-                    };
-                    step(std::integral_constant<int, 0>{}); step(std::integral_constant<int, 1>{});
-                    step(std::integral_constant<int, 2>{}); step(std::integral_constant<int, 3>{});
-                    // t8: lanes q < 4 keep chain 2q and take chain 2q of lane q+4; lanes q >= 4 keep chain 2q+1 and take it from lane q-4
-                    const bool hi4 = q >= 4, b1 = (q & 2) != 0, b0 = (q & 1) != 0;
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (u < UU) {
-                            float a0, a1;
-                            unpack2(acc[u], a0, a1);
-                            v[u] = fadd(hi4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi4 ? a0 : a1, 4, 8));
-                        } else v[u] = 0.0f;
-                    }
-                    // t4: lanes with q & 2 keep pixels 2,3 and send 0,1; the others keep 0,1 and send 2,3
-                    const float w0 = fadd(b1 ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2, 8));
-                    const float w1 = fadd(b1 ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2, 8));
-                    // t2: lanes with q & 1 keep the odd pixel
-                    const float x = fadd(b0 ? w1 : w0, __shfl_xor_sync(0xffffffffu, b0 ? w0 : w1, 1, 8));
-                    const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));      // t2[0] + t2[1]: pixel u = q & 3
-                    const unsigned hu = b1 ? (b0 ? hv[3] : hv[2]) : (b0 ? hv[1] : hv[0]);
-                    if (q < 4 && hu != 255u && cur > flo && cur < fhi)              // strict range test, Raisr.cpp:1192-1196
-                        sts_f32(hroff + 4u * (unsigned)(h * HP + jc0), cur);
-                };
-                // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
-                // single pixel groups over all warps so that no warp waits a whole item at the barrier.  Items without a hashed
-                // pixel (rows outside [6, H-6), columns from c_end on) are skipped: HR stays S there.
-                const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
-                auto live = [&](int h, int jc0) {
-                    const int r = y0 - 1 + h;
-                    return r >= 6 && r < H - 6 && x0 - 1 + jc0 < p.c_end;
-                };
-                for (int it = cwarp; it < nfull; it += NCW) {
-                    const int ri = it / NBLK, bi = it - ri * NBLK;
-                    const int h = hfirst + ri * JS, jc0 = jfirst + bi * 4 * U * JS;
-                    if (!live(h, jc0)) continue;
-                    if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jc0);
-                    else fast_block(std::integral_constant<int, ULAST>{}, h, jc0);
-                }
-                for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
-                    const int it = nfull + rq / U, u = rq - (rq / U) * U;
-                    const int ri = it / NBLK, bi = it - ri * NBLK;
-                    const int h = hfirst + ri * JS, jc0 = jfirst + (bi * 4 * U + 4 * u) * JS;
-                    if ((bi == NBLK - 1 && u >= ULAST) || !live(h, jc0)) continue;
-                    fast_block(std::integral_constant<int, 1>{}, h, jc0);
-                }
-                // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
-                // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
-                if (has_ov && p.blending == 2) {
-                    const int jlo = max(jfirst, p.tail_start - (x0 - 1)), jhi = min(HW, p.tail_start + OVW - (x0 - 1));
-                    const int j0 = jlo + ((jlo - jfirst) % JS != 0 ? JS - (jlo - jfirst) % JS : 0);   // first column of this type in the overlap
-                    const int ncol = (jhi > j0) ? (jhi - j0 + JS - 1) / JS : 0;
-                    const int total = nrows * ncol;
-                    for (int base = cwarp * 4; base < total; base += NCW * 4) {
-                        const int pi = min(base + g, total - 1);
-                        const int ri = pi / ncol, ci = pi - ri * ncol;
-                        const int h = hfirst + ri * JS, j = j0 + ci * JS;
-                        const int hv = sHash[h * HP + j];
-                        const int hv2 = sHash2[h * OVW + (x0 - 1 + j - p.tail_start)];
-                        const float *sp = sS + (h + 1) * SP + j + 1;
-                        const float cur8 = dot8(sp, sF + (hv == 255 ? 0 : hv) * 128, off, q);
-                        const float cur16 = dot8(sp, sF + (hv2 == 255 ? 0 : hv2) * 128, off, q);
-                        const bool ok8 = cur8 > flo && cur8 < fhi;
-                        if (q == 0 && base + g < total && hv != 255 && hv2 != 255 && !ok8 && cur16 > flo && cur16 < fhi) sHR[h * HP + j] = cur16;
-                    }
-                }
-                group_sync(BAR_CONS, NCT);
-            }
-            // ---- E: blend + store ----
-            stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
-            group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
-            if (tile + 2 * (int)gridDim.x < ntiles) named_arrive(BAR_EMPTY + buf, NBT + NCT);   // bucket tile may be refilled (tile i+2)
-            if (p.band_done && ct == 0 && !(p.out_tail && y0 >= p.tail_row0)) {
-                __threadfence();
-                atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
-            }
-        }
-        if (p.chroma_n > 0)
-            while (slices_done < nslices) chroma_slice(slices_done++);       // CTAs with fewer than three tiles
+        pipe_filter_pass<PixT, PT, UPSA, false, F16>(pa, smem_raw, b, cy, tid0);
+        if constexpr (UPSB >= 0) pipe_filter_pass<PixT, PT, UPSB, true, F16>(pb, smem_raw, tileB0, cy, tid0);
     }
 }
 
