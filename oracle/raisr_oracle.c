@@ -390,6 +390,20 @@ int oracle_process_y(const uint16_t *in, int inW, int inH, uint16_t *out, int ou
                      int passes, int mode, const oracle_pass_params *p1, const oracle_pass_params *p2,
                      int32_t *hash1, int32_t *hash2)
 {
+    /* exact ratios: (int)(outH / ratio) == inH */
+    return oracle_process_y_ratio(in, inW, inH, out, outW, outH, (float)outH / (float)inH, passes, mode, p1, p2, hash1, hash2);
+}
+
+/* The reference builds the luma resize for {inW, (int)(segHeight / gRatio)} -> {outW, segHeight} (Raisr.cpp:1801-1803; one band:
+ * segHeight = outH): when outH was truncated (odd input height at 1.5x: 135 -> 202, or vf_raisr's evenoutput) the vertical map is
+ * built for FEWER source rows than the input plane has, and the last input row is never read. */
+int oracle_process_y_ratio(const uint16_t *in, int inW, int inH, uint16_t *out, int outW, int outH, float ratio,
+                           int passes, int mode, const oracle_pass_params *p1, const oracle_pass_params *p2,
+                           int32_t *hash1, int32_t *hash2)
+{
+    int srcH = (int)((float)outH / ratio);
+    if (srcH > inH) srcH = inH;
+    if (srcH < 1) srcH = 1;
     if (passes != 1 && passes != 2) return -1;
     if (passes == 1) mode = 1;                          /* mode 2 is ignored with one pass, Raisr.cpp:1434-1435 */
     int rc = -1;
@@ -397,7 +411,7 @@ int oracle_process_y(const uint16_t *in, int inW, int inH, uint16_t *out, int ou
     if (passes == 1 || mode == 1) {
         up = (uint16_t *)malloc((size_t)outW * outH * sizeof(uint16_t));
         if (!up) return -1;
-        oracle_resize(in, inW, inH, up, outW, outH);
+        oracle_resize(in, inW, srcH, up, outW, outH);
         if (passes == 1) { rc = oracle_pass(up, outW, outH, p1, hash1, NULL, NULL, out); goto done; }
         mid = (uint16_t *)malloc((size_t)outW * outH * sizeof(uint16_t));
         if (!mid) goto done;
@@ -409,7 +423,7 @@ int oracle_process_y(const uint16_t *in, int inW, int inH, uint16_t *out, int ou
         if (!mid || !up) goto done;
         rc = oracle_pass(in, inW, inH, p1, hash1, NULL, NULL, mid);            /* pass 1 at input resolution */
         if (rc != 0) goto done;
-        oracle_resize(mid, inW, inH, up, outW, outH);                           /* pass 2 upscales, Raisr.cpp:945 */
+        oracle_resize(mid, inW, srcH, up, outW, outH);                          /* pass 2 upscales, Raisr.cpp:945 */
         rc = oracle_pass(up, outW, outH, p2, hash2, NULL, NULL, out);
     }
 done:

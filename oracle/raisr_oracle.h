@@ -67,6 +67,10 @@ void oracle_resize(const uint16_t *in, int inW, int inH, uint16_t *out, int outW
 int oracle_process_y(const uint16_t *in, int inW, int inH, uint16_t *out, int outW, int outH,
                      int passes, int mode, const oracle_pass_params *p1, const oracle_pass_params *p2,
                      int32_t *hash1, int32_t *hash2);
+/* same with the reference's ratio made explicit: the resize reads (int)(outH / ratio) source rows (Raisr.cpp:1801-1803) */
+int oracle_process_y_ratio(const uint16_t *in, int inW, int inH, uint16_t *out, int outW, int outH, float ratio,
+                     int passes, int mode, const oracle_pass_params *p1, const oracle_pass_params *p2,
+                     int32_t *hash1, int32_t *hash2);
 
 /* gGaussian2D{8,10,16}bit as a dense 11x11 table (Raisr_globals.h:208-264) */
 void oracle_gaussian_weights(int bits, float *w121);

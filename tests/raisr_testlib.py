@@ -121,6 +121,7 @@ def oracle_lib():
         L = C.CDLL(path)
         L.oracle_pass.restype = C.c_int
         L.oracle_process_y.restype = C.c_int
+        L.oracle_process_y_ratio.restype = C.c_int
         for n in ("oracle_x86_rcp14", "oracle_x86_rsqrt14", "oracle_x86_rcpps", "oracle_x86_rsqrtps"):
             getattr(L, n).restype = C.c_float
             getattr(L, n).argtypes = [C.c_float]
@@ -167,8 +168,12 @@ def oracle_resize(img, outW, outH):
     return out.astype(img.dtype)
 
 
-def oracle_process_y(img, outW, outH, m1, m2=None, passes=1, mode=1, want_hash=False):
+def oracle_process_y(img, outW, outH, m1, m2=None, passes=1, mode=1, want_hash=False, ratio=None):
+    """ratio: the reference's gRatio (1.5 or 2.0); default = the nearest of those to outW / inW.  It matters only when the output
+    size was truncated (odd input at 1.5x, evenoutput): the luma resize then reads (int)(outH / ratio) source rows."""
     L = oracle_lib()
+    if ratio is None:
+        ratio = round(2.0 * outW / img.shape[1]) / 2.0
     a = np.ascontiguousarray(img, dtype=np.uint16)
     inH, inW = a.shape
     out = np.zeros((outH, outW), np.uint16)
@@ -177,8 +182,8 @@ def oracle_process_y(img, outW, outH, m1, m2=None, passes=1, mode=1, want_hash=F
         h1 = np.zeros((inH, inW) if (passes == 2 and mode == 2) else (outH, outW), np.int32)
         h2 = np.zeros((outH, outW), np.int32)
     ptr = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
-    rc = L.oracle_process_y(ptr(a), inW, inH, ptr(out), outW, outH, passes, mode, C.byref(m1.p),
-                            C.byref(m2.p) if m2 is not None else None, ptr(h1), ptr(h2))
+    rc = L.oracle_process_y_ratio(ptr(a), inW, inH, ptr(out), outW, outH, C.c_float(ratio), passes, mode, C.byref(m1.p),
+                                  C.byref(m2.p) if m2 is not None else None, ptr(h1), ptr(h2))
     assert rc == 0
     out = out.astype(img.dtype)
     return (out, h1, h2) if want_hash else out

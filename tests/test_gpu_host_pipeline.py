@@ -208,3 +208,37 @@ def test_setres_rejects_cb_geometry_that_differs_from_cr():
         assert L.RNLHandler_SetRes(*[C.byref(x) for x in bad]) == T.RNLErrorBadParameter
     finally:
         L.RNLHandler_Deinit()
+
+
+@pytest.mark.parametrize("env", [{}, {"RAISR_CUDA_STAGE_PAGEABLE": "0"}, {"RAISR_CUDA_COPY_THREADS": "0"}, {"RAISR_CUDA_COPY_THREADS": "1"},
+                                 {"RAISR_CUDA_NO_MEMOPS": "1"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()) or "default")
+def test_pageable_planes_with_padded_steps_through_the_staging_pipeline(env, monkeypatch):
+    """Pageable caller planes (what av_frame_get_buffer hands a software filter) travel through the engine's page-locked staging
+    planes, moved by the copy threads band by band.  Whatever the thread count or fallback, the frame is the page-locked result,
+    and the bytes between width and step stay untouched."""
+    cfg = CONFIGS[6]
+    folder, ratio, bits, passes, mode, (w, h) = cfg
+    src = planes(w, h, bits, seed=41)
+    want = run_host(cfg, src, pinned=True)
+    oW, oH = int(w * ratio), int(h * ratio)
+    pad = 48
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    eng = B.Engine(T.filter_folder(folder), ratio, bits, T.VideoRange, passes, mode, numerics=B.NUMERICS_AUTO)
+    eng.set_res(w, h, oW, oH, w // 2, h // 2, oW // 2, oH // 2)
+    inb = [np.full((a.shape[0], a.shape[1] + pad), 0x5A, a.dtype) for a in src]
+    for b, a in zip(inb, src):
+        b[:, :a.shape[1]] = a
+    ins = [b[:, :a.shape[1]] for b, a in zip(inb, src)]
+    outb = [np.full((oH, oW + pad), 0xA5, np.uint8), np.full((oH // 2, oW // 2 + pad), 0xA5, np.uint8), np.full((oH // 2, oW // 2 + pad), 0xA5, np.uint8)]
+    outs = [outb[0][:, :oW], outb[1][:, :oW // 2], outb[2][:, :oW // 2]]
+    for _ in range(3):
+        for o in outs:
+            o[...] = 0
+        assert eng.process_host(ins[0], outs[0], ins[1], ins[2], outs[1], outs[2]) == 0
+        for a, b, n in zip(want, outs, "YUV"):
+            assert np.array_equal(a, b), "%s plane differs on %d samples with %r" % (n, (a != b).sum(), env)
+    for b, o in zip(outb, outs):
+        assert (b[:, o.shape[1]:] == 0xA5).all(), "bytes beyond the row width were written"
+    eng.close()

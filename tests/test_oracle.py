@@ -123,3 +123,24 @@ def test_oracle_vs_live_reference(folder, ratio, bits, passes, mode, size):
     if passes == 2:
         assert np.array_equal(h2, ref_h[1])
     assert np.array_equal(out, ref_y)
+
+
+@pytest.mark.skipif(not (T.have_ref() and T.have_avx512()), reason="oracle/_ref not usable on this host")
+@pytest.mark.parametrize("folder,passes,mode,size", [
+    ("filters_1.5x/filters_highres", 1, 1, (211, 135)),        # 135 * 1.5 = 202.5 -> 202 output rows: the resize reads 134 source rows
+    ("filters_1.5x/filters_denoise", 2, 2, (211, 135)),
+    ("filters_1.5x/filters_denoise", 2, 1, (98, 51)),          # (an output width = 1 mod 8 would hit the reference's blend-loop overshoot)
+])
+def test_truncated_output_height_reads_fewer_source_rows_like_the_reference(folder, passes, mode, size):
+    """Raisr.cpp:1801-1803: the luma resize spec is {inW, (int)(outH / ratio)} -> {outW, outH}.  With an odd input height at 1.5x the
+    output height is truncated and the last input row is never read -- pinned here against the compiled reference."""
+    w, h = size
+    img = T.synth_frame(w, h, 8, seed=7000 + w, kind="mix")
+    ref_y, _ = T.run_ref_subprocess(folder, img, ratio=1.5, passes=passes, mode=mode)
+    oW, oH = int(w * 1.5), int(h * 1.5)
+    assert ref_y.shape == (oH, oW)
+    f = T.filter_folder(folder)
+    m1 = T.OracleModel(f, 8, False, T.VideoRange, 1)
+    m2 = T.OracleModel(f, 8, True, T.VideoRange, 1) if passes == 2 else None
+    got = T.oracle_process_y(img, oW, oH, m1, m2, passes, mode, ratio=1.5)
+    assert np.array_equal(got, ref_y), "%d px differ" % (got != ref_y).sum()

@@ -466,7 +466,11 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                 int in_lo, in_hi;
                 tile_input_rows<UPS>(p, y0, th, in_lo, in_hi);
                 const int ty_hi = min(p.dep_ny - 1, (min(in_hi, p.dep_row1 - 1) - p.dep_row0) / p.dep_th);
+#ifdef RAISR_EXP_NO_DEPWAIT
+                if (false) {
+#else
                 if (ty_hi >= dep_known) {
+#endif
                     wait_rows_done(p.dep_done, (unsigned)p.dep_gx, ty_hi, dep_known, p.err_flag, lt == 0, BAR_CHAIN, NBT);
                     dep_known = ty_hi + 1;
                 }
@@ -593,10 +597,13 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
         // seen the flag (leader's ld.acquire -> BAR_CHAIN -> BAR_PROD -> BAR_FULL: causality is cumulative).  The producers run a
         // tile ahead, so the barrier has usually completed long before and nothing is lost.
         bool full_taken = false;
+#ifndef RAISR_EXP_NO_EARLY_FULL
         if (DEP) {
             group_sync(BAR_FULL + buf, NBT + NCT);
             full_taken = true;
-        } else if (p.in_ready && !input_complete) {
+        } else
+#endif
+        if (p.in_ready && !input_complete) {
             int in_lo, in_last;
             tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
             if (in_last >= p.in_split_row) {
