@@ -319,7 +319,13 @@ def load_golden(name):
 
 def golden_names():
     d = os.path.join(ROOT, "tests", "golden")
-    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz") and not f.startswith("ipp_"))
+
+
+def ipp_golden_names():
+    """outputs of REAL Intel IPP for the golden inputs (tools/ipp_pin/; absent until someone with IPP runs it)"""
+    d = os.path.join(ROOT, "tests", "golden")
+    return sorted(f[4:-4] for f in os.listdir(d) if f.endswith(".npz") and f.startswith("ipp_"))
 
 
 def have_avx512():

@@ -79,3 +79,13 @@ def test_replay_of_vf_raisr_matches_the_oracle(folder, ratio, bits, passes, mode
         ref = T.oracle_process_y(y, oW, oH, m1, m2, passes, mode)
         assert np.array_equal(oy, ref), "frame %d: Y differs on %d px" % (n, (oy != ref).sum())
         assert np.array_equal(ou, T.oracle_resize(u, ocw, och)) and np.array_equal(ov, T.oracle_resize(v, ocw, och)), "frame %d chroma" % n
+
+
+def test_cuda_hwframe_filter_source_type_checks_against_ffmpeg_stubs():
+    """ffmpeg/vf_raisr_cuda.c cannot be built here (no libav headers).  tests/harness/ffstub restates the FFmpeg declarations it
+    uses; `gcc -fsyntax-only` against those and include/raisr_cuda.h catches typos, wrong member names and wrong C-ABI calls."""
+    src = os.path.join(T.ROOT, "ffmpeg", "vf_raisr_cuda.c")
+    r = subprocess.run(["gcc", "-std=gnu11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter",
+                        "-Wno-missing-field-initializers", "-I" + os.path.join(T.ROOT, "tests", "harness", "ffstub"),
+                        "-I" + os.path.join(T.ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -587,6 +587,9 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *nm = std::getenv("RAISR_CUDA_NO_MEMOPS")) e->no_memops = std::atoi(nm) != 0;
     if (const char *lb = std::getenv("CUDA_LAUNCH_BLOCKING")) e->no_memops = e->no_memops || std::atoi(lb) != 0;
     if (const char *k = std::getenv("RAISR_CUDA_KERNEL")) e->use_pipe = std::strcmp(k, "tile") != 0;
+    // 16-bit samples (not reachable from the FFmpeg filter: bits = 8..10, vf_raisr.c:83) run on the phase-sequential kernel: the
+    // pipelined kernel reads its Gaussian weights from immutable constant tables that exist for 8 and 10 bit (raisr_gw_tables.h)
+    if (cfg->bit_depth == 16) e->use_pipe = false;
     if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));

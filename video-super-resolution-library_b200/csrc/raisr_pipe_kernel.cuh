@@ -19,6 +19,7 @@
 // STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite, tools/kbench.py); 0.63 ms vs 0.85 ms per 4K frame.
 #pragma once
 #include "raisr_kernels.cuh"
+#include "raisr_gw_tables.h"
 
 namespace raisr {
 
@@ -27,10 +28,11 @@ constexpr int NPW = 16;                      // producer warps: 8 chain warps (s
 constexpr int NCW = NTP / 32 - NPW;          // filter (consumer) warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
 constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
-constexpr int CHAIN_REGS = 48, BUCKET_REGS = 64, CONS_REGS = 88;   // setmaxnreg targets: 256*48 + 256*64 + 384*88 <= 896*72 registers of the CTA
+constexpr int CHAIN_REGS = 56, BUCKET_REGS = 64, CONS_REGS = 88;   // setmaxnreg targets: 256*48 + 256*64 + 384*88 <= 896*72 registers of the CTA
                                                                    // (measured: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms)
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
+static_assert(RBP * SW <= 2 * NBT && RBP * SW > NBT, "generic ring refill: one or two samples per chain thread");
 static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
 
 constexpr int PTH_MAX = 46;                  // output tile height of the pipelined kernel (smaller than TH_MAX: the chain buffer is double-buffered)
@@ -331,9 +333,14 @@ static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigne
 
 // =========================== producers: buckets of tile i -> bucket tile [i & 1] ===========================
 // chain warps (stage B) and bucket warps (stage C) of one pass; tid = thread index inside the producer group
+// The Gaussian weights come from immutable constant tables selected by the sample type (raisr_gw_tables.h: 8-bit and 10-bit; 16-bit
+// samples run on the phase-sequential kernel): compile-time constant-bank addresses, i.e. uniform operands of FMUL2 in both inlined
+// copies of this function.  (Read from the parameter block, the second copy of a chained launch staged all 66 weights through
+// registers and spilled them inside the column-chain loop: 1.50 ms instead of 1.21 ms for the two passes at 1080p->4K.)
 template <typename PixT, int PT, int UPS, bool DEP>
 __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int tid)
 {
+    const float (&gw)[6][6] = (sizeof(PixT) == 1) ? c_gw8 : c_gw10;
     uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
     float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
     float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
@@ -399,7 +406,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                 const f32x2 gx2 = pack2(gxv, gxv), gy2 = pack2(gyv, gyv);
 #pragma unroll
                 for (int mm = 0; mm < 3; ++mm) {
-                    const f32x2 w2 = pack2(p.gw[i][2 * mm], p.gw[i][2 * mm + 1]);
+                    const f32x2 w2 = pack2(gw[i < 6 ? i : 10 - i][2 * mm], gw[i < 6 ? i : 10 - i][2 * mm + 1]);   // rows i and 10-i share their weights
                     const f32x2 px = mul2(gx2, w2), py = mul2(gy2, w2);  // round(g * w), Raisr_AVX512.cpp:64-67
                     acc[mm][0] = fma2(px, gx2, acc[mm][0]);
                     acc[mm][1] = fma2(px, gy2, acc[mm][1]);
@@ -495,16 +502,27 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
             for (int k = 0; k < nchunks; ++k) {
                 const bool more = k + 1 < nchunks;
                 unsigned pab = 0u, pcd = 0u;
-                if (UPS == 1 && more && lt < SW / 2) load_block(RBP * k + RING - RBP, lt, y0, x0, pab, pcd);
+                float pv0 = 0.0f, pv1 = 0.0f;
+                // the two ring rows of the NEXT chunk: global loads issued before stage B, stored after it (latency hidden).  Other
+                // ratios: one sample per thread (+ a second one for the first RBP*SW - NBT threads); the tile origin is made opaque
+                // per chunk so that the compiler recomputes the few address terms instead of keeping them live across stage B
+                // (48 registers: hoisted invariants spilled INSIDE the chain loop of the chained kernel).
+                int y0v = y0, x0v = x0;
+                if (UPS != 1) asm volatile("" : "+r"(y0v), "+r"(x0v));
+                const int snext = RBP * k + RING - RBP;
+                if (UPS == 1) {
+                    if (more && lt < SW / 2) load_block(snext, lt, y0, x0, pab, pcd);
+                } else if (more) {
+                    pv0 = sample_S<PixT, UPS>(p, y0v - 7 + snext + lt / SW, x0v - 7 + lt % SW);
+                    if (lt < RBP * SW - NBT) pv1 = sample_S<PixT, UPS>(p, y0v - 7 + snext + (lt + NBT) / SW, x0v - 7 + (lt + NBT) % SW);
+                }
                 stage_B(k);
                 if (more) {
                     if (UPS == 1) {
-                        if (lt < SW / 2) store_block(RBP * k + RING - RBP, lt, pab, pcd);
+                        if (lt < SW / 2) store_block(snext, lt, pab, pcd);
                     } else {
-                        for (int idx = lt; idx < RBP * SW; idx += NBT) {
-                            const int s = RBP * k + RING - RBP + idx / SW, sx = idx % SW;
-                            sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
-                        }
+                        sRing[((snext + lt / SW) & (RING - 1)) * SP + lt % SW] = pv0;
+                        if (lt < RBP * SW - NBT) sRing[((snext + (lt + NBT) / SW) & (RING - 1)) * SP + (lt + NBT) % SW] = pv1;
                     }
                 }
                 group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
