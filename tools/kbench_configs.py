@@ -19,7 +19,7 @@ for name, folder, ratio, bits, passes, mode, w, h in CONFIGS:
     tdt = torch.uint8 if bits == 8 else torch.int16
     ys = [torch.from_numpy(T.synth_frame(w, h, bits, 1234 + i).view(np.int16) if bits != 8 else T.synth_frame(w, h, bits, 1234 + i)).cuda() for i in range(NB)]
     outs = [torch.empty((oH, oW), dtype=tdt, device="cuda") for _ in range(NB)]
-    eng = B.Engine(T.filter_folder(folder), ratio, bits, 1, passes, mode, device=0, numerics=B.NUMERICS_AUTO)
+    eng = B.Engine(T.filter_folder(folder), ratio, bits, 1, passes, mode, device=0, numerics=int(os.environ.get("RAISR_KB_NUMERICS", B.NUMERICS_AUTO)))
     eng.set_res(w, h, oW, oH)
     bps = 1 if bits == 8 else 2
     def run(i):

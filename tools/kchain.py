@@ -21,7 +21,7 @@ for name, folder, ratio, bits, passes, mode, w, h in CONFIGS:
     ys = [torch.from_numpy(fr[i % 2].view(np.int16) if bits != 8 else fr[i % 2]).cuda() for i in range(NB)]
     outs = [torch.empty((oH, oW), dtype=tdt, device="cuda") for _ in range(NB)]
     os.dup2(fd, 1)
-    eng = B.Engine(T.filter_folder(folder), ratio, bits, 1, passes, mode, device=0, numerics=B.NUMERICS_AUTO)
+    eng = B.Engine(T.filter_folder(folder), ratio, bits, 1, passes, mode, device=0, numerics=int(os.environ.get("RAISR_KB_NUMERICS", B.NUMERICS_AUTO)))
     os.dup2(saved, 1)
     eng.set_res(w, h, oW, oH)
     bps = 1 if bits == 8 else 2

@@ -32,7 +32,6 @@ constexpr int CHAIN_REGS = 56, BUCKET_REGS = 64, CONS_REGS = 88;   // setmaxnreg
                                                                    // (measured: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms)
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
-static_assert(RBP * SW <= 2 * NBT && RBP * SW > NBT, "generic ring refill: one or two samples per chain thread");
 static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
 
 constexpr int PTH_MAX = 46;                  // output tile height of the pipelined kernel (smaller than TH_MAX: the chain buffer is double-buffered)
@@ -502,27 +501,18 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
             for (int k = 0; k < nchunks; ++k) {
                 const bool more = k + 1 < nchunks;
                 unsigned pab = 0u, pcd = 0u;
-                float pv0 = 0.0f, pv1 = 0.0f;
-                // the two ring rows of the NEXT chunk: global loads issued before stage B, stored after it (latency hidden).  Other
-                // ratios: one sample per thread (+ a second one for the first RBP*SW - NBT threads); the tile origin is made opaque
-                // per chunk so that the compiler recomputes the few address terms instead of keeping them live across stage B
-                // (48 registers: hoisted invariants spilled INSIDE the chain loop of the chained kernel).
-                int y0v = y0, x0v = x0;
-                if (UPS != 1) asm volatile("" : "+r"(y0v), "+r"(x0v));
-                const int snext = RBP * k + RING - RBP;
-                if (UPS == 1) {
-                    if (more && lt < SW / 2) load_block(snext, lt, y0, x0, pab, pcd);
-                } else if (more) {
-                    pv0 = sample_S<PixT, UPS>(p, y0v - 7 + snext + lt / SW, x0v - 7 + lt % SW);
-                    if (lt < RBP * SW - NBT) pv1 = sample_S<PixT, UPS>(p, y0v - 7 + snext + (lt + NBT) / SW, x0v - 7 + (lt + NBT) % SW);
-                }
+                if (UPS == 1 && more && lt < SW / 2) load_block(RBP * k + RING - RBP, lt, y0, x0, pab, pcd);
                 stage_B(k);
                 if (more) {
                     if (UPS == 1) {
-                        if (lt < SW / 2) store_block(snext, lt, pab, pcd);
+                        if (lt < SW / 2) store_block(RBP * k + RING - RBP, lt, pab, pcd);
                     } else {
-                        sRing[((snext + lt / SW) & (RING - 1)) * SP + lt % SW] = pv0;
-                        if (lt < RBP * SW - NBT) sRing[((snext + (lt + NBT) / SW) & (RING - 1)) * SP + (lt + NBT) % SW] = pv1;
+                        // (measured: fetching these samples before stage B like the 2x path costs more registers than the latency
+                        // it hides -- 0.326 instead of 0.289 ms for the two 1.5x passes at 720p)
+                        for (int idx = lt; idx < RBP * SW; idx += NBT) {
+                            const int s = RBP * k + RING - RBP + idx / SW, sx = idx % SW;
+                            sRing[(s & (RING - 1)) * SP + sx] = sample_S<PixT, UPS>(p, y0 - 7 + s, x0 - 7 + sx);
+                        }
                     }
                 }
                 group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
