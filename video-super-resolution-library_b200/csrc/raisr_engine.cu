@@ -878,6 +878,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     const size_t user_ostep[3] = {out_y_step, out_u_step, out_v_step};
     const size_t orow[3] = {e->out_w * bps, e->out_cw * bps, e->out_cw * bps};
     const int orows[3] = {e->out_h, e->out_ch, e->out_ch};
+    bool late_inputs = false;                                           // staged input rows that are still being copied at launch time
     if (stage_in || stage_out) {
         if (!e->pool) { e->pool = new CopyPool; e->pool->start(e->copy_threads, e->device, e->bind_device); }
         const size_t irow[3] = {e->in_w * bps, e->in_cw * bps, e->in_cw * bps};
@@ -887,19 +888,25 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
             if (stage_out && !e->h_stage_out[i]) CUDA_OK(cudaHostAlloc(&e->h_stage_out[i], orow[i] * orows[i], cudaHostAllocDefault));
         }
         if (stage_in) {
-            // all input bytes before anything is enqueued (every copy the kernel waits for is enqueued before the launch): ~3 MB
+            // Without stream memory operations every input byte is staged before anything is enqueued.  With them only the luma
+            // rows the first tiles read are staged up front; the copy threads stage the rest (~3 MB) while this thread enqueues
+            // the first H2D copy and launches the kernel, which waits in-kernel (bounded) for the flags behind the late copies.
             const void *src[3] = {in_y, in_u, in_v};
             const size_t sstep[3] = {in_y_step, in_u_step, in_v_step};
+            late_inputs = memops && e->split_h2d && e->in_h >= 256;
+            const int early_rows = late_inputs ? std::max(64, (e->in_h / 8 + 15) & ~15) : 0;
             const int parts = std::max(1, e->copy_threads);
             for (int i = 0; i < (chroma ? 3 : 1); ++i)
                 for (int k = 0; k < (i == 0 ? parts : 1); ++k) {
-                    const int n = i == 0 ? parts : 1, r0 = (int)((long long)irows[i] * k / n), r1 = (int)((long long)irows[i] * (k + 1) / n);
+                    const int first = i == 0 ? early_rows : 0, n = i == 0 ? parts : 1;
+                    const int r0 = first + (int)((long long)(irows[i] - first) * k / n), r1 = first + (int)((long long)(irows[i] - first) * (k + 1) / n);
                     void *dst = static_cast<char *>(e->h_stage_in[i]) + (size_t)r0 * irow[i];
                     const void *sp = static_cast<const char *>(src[i]) + (size_t)r0 * sstep[i];
                     const size_t ss = sstep[i], rb = irow[i];
                     e->pool->submit([dst, sp, ss, rb, r0, r1] { copy_rows(dst, rb, sp, ss, rb, r1 - r0); });
                 }
-            e->pool->wait_all();
+            if (early_rows) copy_rows(e->h_stage_in[0], irow[0], in_y, in_y_step, irow[0], early_rows);
+            if (!late_inputs) e->pool->wait_all();
             in_y = e->h_stage_in[0]; in_y_step = irow[0];
             if (chroma) { in_u = e->h_stage_in[1]; in_v = e->h_stage_in[2]; in_u_step = in_v_step = irow[1]; }
         }
@@ -936,19 +943,8 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     if (e->timing) cudaEventRecord(e->tev[0], e->stream);
     CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, rows0, cudaMemcpyHostToDevice, e->stream));
     if (e->timing) cudaEventRecord(e->tev[1], e->stream);
-    if (split_row) {
-        CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));                      // part 2 behind part 1 (same copy engine anyway)
-        CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
-        CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
-                                  static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
-                                  cudaMemcpyHostToDevice, e->stream_h2d));
-        if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
-        if (chroma) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));      // the chroma copies queue up behind the luma copies
-    } else if (chroma) {
-        CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
-    }
-
-    // ---- chroma input ------------------------------------------------------------------------------------------------
+    // luma rows >= split_row and the chroma planes: on their own streams, each followed by the flag the kernel waits for.  Enqueued
+    // before the launch -- unless their staging copies are still running (late_inputs): then right after it.
     ChromaJob cj{};
     if (chroma) {
         for (int i = 0; i < 2; ++i) {
@@ -958,16 +954,38 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         if (memops) {
             cj.ready = e->d_chroma_ready; cj.seq = ++e->chroma_seq;          // H2D on the chroma stream, flagged to the running kernel
             cj.done = e->d_chroma_ready + 1;                                 // D2H by the copy engine as soon as every CTA has written its share
-            CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
-            for (int i = 0; i < 2; ++i)
-                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
-                                          cudaMemcpyHostToDevice, e->stream_uv));
-            if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
-        } else {
-            for (int i = 0; i < 2; ++i)
-                CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
-                                          cudaMemcpyHostToDevice, e->stream));
         }
+    }
+    if (split_row) CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));           // part 2 behind part 1 (same copy engine anyway)
+    auto enqueue_rest_of_input = [&]() -> int {
+        if (split_row) {
+            CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
+            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
+                                      static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
+                                      cudaMemcpyHostToDevice, e->stream_h2d));
+            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+            if (chroma) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));  // the chroma copies queue up behind the luma copies
+        } else if (chroma) {
+            CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
+        }
+        if (chroma) {
+            if (memops) {
+                CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
+                for (int i = 0; i < 2; ++i)
+                    CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
+                                              cudaMemcpyHostToDevice, e->stream_uv));
+                if (e->write_value32(e->stream_uv, (unsigned long long)(uintptr_t)e->d_chroma_ready, cj.seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+            } else {
+                for (int i = 0; i < 2; ++i)
+                    CUDA_OK(cudaMemcpy2DAsync(e->d_in[i + 1].ptr, e->d_in[i + 1].pitch, csrc[i], csstep[i], e->in_cw * bps, e->in_ch,
+                                              cudaMemcpyHostToDevice, e->stream));
+            }
+        }
+        return 0;
+    };
+    if (!late_inputs) {
+        const int rc_in = enqueue_rest_of_input();
+        if (rc_in) return rc_in;
     }
     for (unsigned i = 0; i < e->cfg.passes; ++i)
         if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], e->stream));
@@ -981,6 +999,11 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
                       tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step, split_row);
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+    if (late_inputs) {                                                      // the kernel is running on the early rows: now the rest
+        e->pool->wait_all();
+        const int rc_in = enqueue_rest_of_input();
+        if (rc_in) return rc_in;
+    }
 
     // ---- chroma output -----------------------------------------------------------------------------------------------------
     if (chroma) {

@@ -28,8 +28,18 @@ constexpr int NPW = 16;                      // producer warps: 8 chain warps (s
 constexpr int NCW = NTP / 32 - NPW;          // filter (consumer) warps (3 warpgroups)
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
 constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
-constexpr int CHAIN_REGS = 56, BUCKET_REGS = 64, CONS_REGS = 88;   // setmaxnreg targets: 256*48 + 256*64 + 384*88 <= 896*72 registers of the CTA
+#ifndef RAISR_CHAIN_REGS
+#define RAISR_CHAIN_REGS 48
+#endif
+#ifndef RAISR_BUCKET_REGS
+#define RAISR_BUCKET_REGS 56
+#endif
+#ifndef RAISR_CONS_REGS
+#define RAISR_CONS_REGS 96
+#endif
+constexpr int CHAIN_REGS = RAISR_CHAIN_REGS, BUCKET_REGS = RAISR_BUCKET_REGS, CONS_REGS = RAISR_CONS_REGS;   // setmaxnreg targets: 256*56 + 256*64 + 384*88 == 896*72 registers of the CTA
                                                                    // (measured: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms)
+static_assert(NBT * (CHAIN_REGS + BUCKET_REGS) + NCT * CONS_REGS <= NTP * 72, "register file of the CTA");
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
 constexpr int RING = 16;                     // rows of the producer's S ring (>= RBP + 12, power of two)
 static_assert(RBP * QW == NBT && RING == 2 * RBP + 12 && (RING & (RING - 1)) == 0 && RBP == 2 && SW % 2 == 0, "producer geometry");
