@@ -467,16 +467,41 @@ def main():
     kern_ms = wl.time_device(wl.luma_only, nk) / nk
     clocks = sampler.stop() if sampler else None
 
-    # end to end through the plugin call with page-locked host planes
+    # end to end through the plugin call with page-locked host planes.  N > 1: the world * K steps of the job are handed out from a
+    # shared counter (frames are independent: a frame-parallel deployment dispatches them to whichever GPU is free), because the
+    # host feed is NOT the same for every GPU of the box (tools/hostfeed_probe.py: 945 vs 1450 frames/s per GPU with all 8 active).
     hs = HandlerSession(wl, pinned=True)
     for _ in range(max(1, args.warmup) * FRAMES_PER_STEP):
         hs.frame()
+    store = None
+    if world > 1:
+        try:
+            store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29500")) + 7, world,
+                                  is_master=(rank == 0), timeout=__import__("datetime").timedelta(seconds=60))
+        except Exception:
+            store = None
+    dispatch = "dynamic (steps from a shared counter)" if store is not None else "static (K steps per rank)"
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps * FRAMES_PER_STEP):
-        hs.frame()
+    my_steps = 0
+    if store is not None:
+        while store.add("e2e_step", 1) <= world * args.steps:
+            for _ in range(FRAMES_PER_STEP):
+                hs.frame()
+            my_steps += 1
+    else:
+        for _ in range(args.steps * FRAMES_PER_STEP):
+            hs.frame()
+        my_steps = args.steps
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    steps_per_rank = None
+    if world > 1:
+        st = torch.tensor([my_steps], dtype=torch.int64, device=dev)
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        steps_per_rank = [int(x.item()) for x in allst]
+        assert sum(steps_per_rank) == world * args.steps
     # the frame the last call filled equals the device-resident result for the same input (not a cached / skipped frame)
     k = (hs.n - 1) % wl.nbuf
     wl.n = k
@@ -565,7 +590,8 @@ def main():
                        "l2": "rotating 12 distinct frame sets (%.0f MB > 126 MB L2)" % (12 * (BYTES_Y + BYTES_C) / 1e6),
                        "numerics": "x86-exact (bit-identical to the compiled reference)" if numerics == 1 else "ieee",
                        "numa": numa},
-            "e2e": {"value": e2e, "unit": "frames/s", "api": "RNLHandler_Process, page-locked host planes",
+            "e2e": {"value": e2e, "unit": "frames/s", "api": "RNLHandler_Process, page-locked host planes", "dispatch": dispatch,
+                    "steps_per_rank": steps_per_rank,
                     "h2d_bytes_per_step": world * FRAMES_PER_STEP * (w * h + 2 * (w // 2) * (h // 2)),
                     "d2h_bytes_per_step": world * FRAMES_PER_STEP * (oW * oH + 2 * (oW // 2) * (oH // 2))},
             "e2e_pageable": {"value": e2e_pageable, "unit": "frames/s", "api": "RNLHandler_Process, pageable host planes (malloc)"},
@@ -680,6 +706,42 @@ def rowband_leg(B, torch, dist, dev, local, rank, world, sptr, stream, max_over_
         e1.record(stream)
         torch.cuda.synchronize()
         single_ms = e0.elapsed_time(e1) / nf
+    # ---- peer-store variant: every rank's band is written by its pass kernel straight into rank 0's frame buffer (NVLink peer
+    # memory, CUDA IPC handle), tile by tile while the band is computed: no gather, no copy after the kernel ----
+    peer = None
+    try:
+        frame0 = torch.zeros((oH, oW), dtype=torch.int16, device=dev) if rank == 0 else None
+        handles = [B.ipc_export(frame0.data_ptr()) if rank == 0 else None]
+        dist.broadcast_object_list(handles, src=0)
+        remote = frame0.data_ptr() if rank == 0 else B.ipc_open(handles[0])
+
+        def band_peer():
+            assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * 2, remote, oW * 2, r0, r1, 2, sptr) == 0
+
+        band_peer()
+        barrier()
+        peer_parity = None
+        if rank == 0:
+            full = torch.zeros((oH, oW), dtype=torch.int16, device=dev)
+            assert eng.process_device_rows(d_in.data_ptr(), d_in.stride(0) * 2, full.data_ptr(), full.stride(0) * 2, 0, oH, 2, sptr) == 0
+            torch.cuda.synchronize()
+            peer_parity = bool(torch.equal(frame0, full))
+            assert peer_parity, "peer-store frame differs from the single-GPU frame"
+        for _ in range(3):
+            band_peer()
+        barrier()
+        e0.record(stream)
+        for _ in range(nf):
+            band_peer()
+        e1.record(stream)
+        barrier()
+        peer = {"ms_per_frame": max_over_ranks(e0.elapsed_time(e1)) / nf, "parity": peer_parity,
+                "how": "out_y of raisr_cuda_process_device_rows = rank 0's frame buffer opened through a CUDA IPC handle; the stage-E stores of "
+                       "every tile go over NVLink while the band is computed; no collective, frame complete at the kernels' end"}
+        if rank != 0:
+            B.ipc_close(remote, handles[0])
+    except Exception as ex:
+        peer = {"error": repr(ex)}
     barrier()
     eng.close()
     # pass-1 rows a band recomputes beyond its own share (mode 2: pass 1 runs at input resolution): +-7 output rows -> /2 + 2
@@ -687,6 +749,7 @@ def rowband_leg(B, torch, dist, dev, local, rank, world, sptr, stream, max_over_
     m0, m1 = max(0, lo // 2 - 2), min(h, -(-hi // 2) + 2)
     return {"workload": c["workload"], "scaling": "strong", "bands": world, "rows_per_band": rows, "parity": parity,
             "ms_per_frame": total_ms, "ms_per_frame_compute_only": compute_ms, "single_gpu_ms_per_frame": single_ms,
+            "peer_store": peer,
             "recompute_rows": {"pass1_rows_per_band": m1 - m0, "own_share": h // world},
             "collective": "NCCL gather of the finished bands to rank 0 (%d bytes per band); no halo exchange" % (rows * oW * 2)}
 

@@ -80,6 +80,18 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
 int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, void *out_y,
                                    size_t out_y_step, int blending, unsigned row0, unsigned row1, void *stream);
 
+/* Peer-store row bands: a rank may pass, as out_y of raisr_cuda_process_device_rows, a pointer into ANOTHER GPU's frame buffer
+ * (same node, NVLink/NVSwitch peer memory).  Its band is then written by the pass kernel's own stores straight into the
+ * gathering GPU's memory, tile by tile while the band is being computed -- no collective, no copy after the kernel.  With one
+ * process per GPU the buffer crosses the process boundary as a CUDA IPC handle: the owner exports it, the peers open it.
+ * (The reference's bands live in one address space, Raisr.cpp:1738-1779; this is the multi-GPU form of "every band writes its
+ * rows of the one output frame".)  handle = 64 opaque bytes (cudaIpcMemHandle_t).
+ * An IPC handle names a whole allocation: *offset = distance of device_ptr from the allocation's base (sub-allocators such as
+ * PyTorch's hand out interior pointers); raisr_cuda_ipc_open returns base + offset in the opening process. */
+int raisr_cuda_ipc_export(void *device_ptr, unsigned char handle[64], size_t *offset);
+int raisr_cuda_ipc_open(const unsigned char handle[64], size_t offset, void **device_ptr);
+int raisr_cuda_ipc_close(void *device_ptr);
+
 /* Bucket plane (int32, -1 where a pixel is not hashed) of pass 0 or 1 of the last frame -> host memory,
  * w*h entries with w,h the plane that pass ran on.  Needs cfg.keep_hash. */
 int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count);

@@ -45,8 +45,37 @@ def lib():
         L.raisr_cuda_destroy.restype = None
         L.raisr_cuda_destroy.argtypes = [vp]
         L.raisr_cuda_version.restype = C.c_char_p
+        for n in ("raisr_cuda_ipc_export", "raisr_cuda_ipc_open", "raisr_cuda_ipc_close"):
+            getattr(L, n).restype = C.c_int32
+        L.raisr_cuda_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(sz)]
+        L.raisr_cuda_ipc_open.argtypes = [C.c_char_p, sz, C.POINTER(vp)]
+        L.raisr_cuda_ipc_close.argtypes = [vp]
         _lib = L
     return _lib
+
+
+def ipc_export(device_ptr):
+    """64-byte CUDA IPC handle of a device allocation (peer-store row bands: the gathering rank exports its frame buffer)"""
+    buf = C.create_string_buffer(64)
+    off = C.c_size_t(0)
+    rc = lib().raisr_cuda_ipc_export(device_ptr, buf, C.byref(off))
+    if rc != 0:
+        raise RuntimeError("raisr_cuda_ipc_export failed: 0x%08x" % (rc & 0xffffffff))
+    return buf.raw, int(off.value)
+
+
+def ipc_open(handle_and_offset):
+    """device pointer (int) in THIS process for another process's exported allocation (+ the exporter's interior offset)"""
+    handle, off = handle_and_offset
+    p = C.c_void_p()
+    rc = lib().raisr_cuda_ipc_open(handle, off, C.byref(p))
+    if rc != 0:
+        raise RuntimeError("raisr_cuda_ipc_open failed: 0x%08x" % (rc & 0xffffffff))
+    return p.value
+
+
+def ipc_close(ptr, handle_and_offset):
+    lib().raisr_cuda_ipc_close(ptr - handle_and_offset[1])
 
 
 class Engine:

@@ -1097,6 +1097,47 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     return rc;
 }
 
+int raisr_cuda_ipc_export(void *device_ptr, unsigned char handle[64], size_t *offset)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size of the C ABI");
+    if (!device_ptr || !handle || !offset) return RNLErrorBadParameter;
+    // base of the allocation device_ptr lies in (cuMemGetAddressRange through the runtime's driver entry point lookup)
+    typedef int (*GetRangeFn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess ||
+        reinterpret_cast<GetRangeFn>(fn)(&base, &size, (unsigned long long)(uintptr_t)device_ptr) != 0) {
+        cudaGetLastError();
+        return RNLErrorUndefined;
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t)base)));
+    memcpy(handle, &h, sizeof(h));
+    *offset = (size_t)((uintptr_t)device_ptr - (uintptr_t)base);
+    return RNLErrorNone;
+}
+
+int raisr_cuda_ipc_open(const unsigned char handle[64], size_t offset, void **device_ptr)
+{
+    if (!handle || !device_ptr) return RNLErrorBadParameter;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *base = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *device_ptr = static_cast<char *>(base) + offset;
+    return RNLErrorNone;
+}
+
+int raisr_cuda_ipc_close(void *device_ptr)
+{
+    // (the pointer returned by raisr_cuda_ipc_open minus its offset: callers keep the pair; closing an interior pointer is an error)
+    if (!device_ptr) return RNLErrorBadParameter;
+    CUDA_OK(cudaIpcCloseMemHandle(device_ptr));
+    return RNLErrorNone;
+}
+
 int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size_t count)
 {
     if (!e || pass < 0 || pass > 1 || !e->d_hash[pass] || !host_out) return RNLErrorBadParameter;
