@@ -1090,8 +1090,20 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     int rc = e->use_pipe ? process_host_pipe(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma)
                          : process_host_tile(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma);
     if (rc == RNLErrorNone && *reinterpret_cast<volatile unsigned *>(e->h_err) != 0) {
-        std::cout << "[RAISR ERROR] a copy the kernel was waiting for never arrived (flag wait timed out)" << std::endl;
-        rc = RNLErrorUndefined;
+        // An in-kernel flag wait ran into its bound: the copy behind the flag never made progress while the kernel was running.
+        // That is what tools that serialise the GPU do (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING): re-run the frame in plain
+        // stream order and stay there for the rest of this engine's life.  A second failure is an error.
+        resync_after_failure(e);
+        if (e->use_pipe && !e->no_memops) {
+            std::cout << "[RAISR WARNING] a copy the kernel was waiting for made no progress under the running kernel (profiler / "
+                         "serialised GPU?): switching this engine to plain stream order (RAISR_CUDA_NO_MEMOPS=1)" << std::endl;
+            e->no_memops = true;
+            rc = process_host_pipe(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma);
+            if (rc == RNLErrorNone && *reinterpret_cast<volatile unsigned *>(e->h_err) != 0) rc = RNLErrorUndefined;
+        } else {
+            rc = RNLErrorUndefined;
+        }
+        if (rc != RNLErrorNone) std::cout << "[RAISR ERROR] a copy the kernel was waiting for never arrived (flag wait timed out)" << std::endl;
     }
     if (rc != RNLErrorNone) resync_after_failure(e);
     return rc;
