@@ -11,7 +11,7 @@ spec = importlib.util.spec_from_file_location("b", os.path.join(T.PKG_DIR, "bind
 w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (300, 200)
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 y = T.synth_frame(w, h, 8, 3); u = T.synth_chroma(w//2, h//2, 8, 4); v = T.synth_chroma(w//2, h//2, 8, 5)
-eng = B.Engine(T.filter_folder("filters_2x/filters_highres"), 2.0, 8, 1, passes, 1, device=0, numerics=B.NUMERICS_AUTO)
+eng = B.Engine(T.filter_folder("filters_2x/filters_highres"), 2.0, 8, 1, passes, 1, device=0, numerics=int(sys.argv[4]) if len(sys.argv) > 4 else B.NUMERICS_AUTO)
 eng.set_res(w, h, 2*w, 2*h, w//2, h//2, w, h)
 oy = np.zeros((2*h, 2*w), np.uint8); ou = np.zeros((h, w), np.uint8); ov = np.zeros((h, w), np.uint8)
 for _ in range(1 if len(sys.argv) > 2 else 2):

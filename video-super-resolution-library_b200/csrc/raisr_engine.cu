@@ -652,6 +652,15 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         auto nr = [](float r, float den) { const float t = r * den; const float e2 = r * t; return (r + r) - e2; };
         e->quarter = nr(x86_rcpps(xt.rcpps, 4.0f), 4.0f);
         e->half = nr(x86_rcpps(xt.rcpps, 2.0f), 2.0f);
+        // the kernels keep the two 14-bit tables packed as ((c0 >> 6) << 10) | c1 in shared memory (raisr_kernels.cuh: lut14)
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t *tb = t ? xt.rcp14 : xt.rsqrt14;
+            for (int i = 0; i < 128; ++i)
+                if ((tb[2 * i] & 63u) != 0 || (tb[2 * i] >> 6) >= (1u << 22) || tb[2 * i + 1] >= 1024u) {
+                    std::cout << "[RAISR ERROR] x86 numerics tables do not fit the packed form" << std::endl;
+                    return fail(RNLErrorBadParameter);
+                }
+        }
         const void *src[4] = {xt.rsqrt14, xt.rcp14, xt.rsqrtps, xt.rcpps};
         const size_t bytes[4] = {kRsqrt14Words * sizeof(uint32_t), kRcp14Words * sizeof(uint32_t), kRsqrtpsEntries * sizeof(uint16_t),
                                  kRcppsEntries * sizeof(uint16_t)};

@@ -112,7 +112,7 @@ constexpr size_t OFF_F = (OFF_HR + sizeof(float) * HH * HP + 127) & ~(size_t)127
 constexpr size_t OFF_HASH = OFF_F + sizeof(float) * SLICE_FLOATS;
 constexpr size_t OFF_HASH2 = OFF_HASH + (size_t)HH * HP;
 constexpr size_t OFF_LUT = (OFF_HASH2 + (size_t)HH * OVW + 15) & ~(size_t)15;    // 256 x uint2: rsqrt14 runs, rcp14 runs
-constexpr size_t OFF_MBAR = OFF_LUT + 256 * sizeof(uint2);
+constexpr size_t OFF_MBAR = OFF_LUT + 2 * 128 * 4 * sizeof(unsigned);
 constexpr size_t SMEM_BYTES = OFF_MBAR + 16;
 static_assert(QW == 128 && HH % RB == 0 && SP >= SW && TW % 4 == 0 && HP % 4 == 0, "tile geometry");
 constexpr int LRW = SW / 2 + 1, LRP = LRW + 1;   // low-res tile of the 2x fast path (lives in the slice buffer during stage A)
@@ -213,25 +213,43 @@ __host__ __device__ __forceinline__ float x86_rcp14(const uint2 *t, float x)
 //   x86_sqrt14(z) = vrcp14ps(vrsqrt14ps(z)) for z = +0 (-> inf -> 0), z < 0 or NaN (-> NaN) and positive normal z;
 //   x86_rcp14_pos(d) = vrcp14ps(d) for positive normal d.  The hash only divides by sums that are >= 1e-17 or NaN, and
 //   whenever the divisor is NaN so is the dividend, hence the quotient is NaN whatever finite pattern this returns.
-__device__ __forceinline__ float x86_rcp14_pos(const uint2 *t, float x)
+// The two 14-bit tables live in shared memory PACKED and REPLICATED: entry e of a table is the word ((c0 >> 6) << 10) | c1
+// (c0 is a multiple of 64 and < 2^25, c1 < 1024: checked where the tables are uploaded) and is stored four times, at words
+// 4e + r, r = 0..3; a lane reads replica r = lane & 3 (the table pointers of HashCtx already point at it).  One 32-bit load per
+// lookup instead of a 64-bit one, and two lanes can only collide when they use the same replica AND their entries differ by a
+// multiple of 8: the eight lookups per pixel took 11.6 M of the kernel's 127 M shared-memory wavefronts, 6.7 M of them bank
+// conflicts (profiles/r2_pipe_kernel_summary.txt).
+constexpr int LUT_WORDS = 2 * 128 * 4;         // rsqrt14 then rcp14
+__device__ __forceinline__ unsigned lut14(const unsigned *t, unsigned entry, unsigned low9)
+{
+    const unsigned w = t[entry * 4u];
+    return (((w >> 10) << 6) - (w & 1023u) * low9) >> 9;
+}
+__device__ __forceinline__ void lut14_fill(unsigned *dst, const uint2 *rsqrt14, const uint2 *rcp14, int tid, int nthreads)
+{
+    for (int i = tid; i < LUT_WORDS; i += nthreads) {
+        const uint2 c = (i < LUT_WORDS / 2) ? rsqrt14[(i >> 2) & 127] : rcp14[(i >> 2) & 127];
+        dst[i] = ((c.x >> 6) << 10) | c.y;
+    }
+}
+
+__device__ __forceinline__ float x86_rcp14_pos(const unsigned *t, float x)
 {
     const unsigned u = __float_as_uint(x);
     const unsigned e8 = u >> 23, m = u & 0x7fffffu;
-    const uint2 c = t[(m >> 16) & 127u];
-    const unsigned v = (c.x - c.y * ((m >> 7) & 0x1ffu)) >> 9;
+    const unsigned v = lut14(t, (m >> 16) & 127u, (m >> 7) & 0x1ffu);
     const unsigned r = (m == 0u) ? 0x7f000000u : (0x7e800000u + (v << 7));
     return __uint_as_float(r - (e8 << 23));
 }
 
-__device__ __forceinline__ float x86_sqrt14(const uint2 *trsq, const uint2 *trcp, float z)
+__device__ __forceinline__ float x86_sqrt14(const unsigned *trsq, const unsigned *trcp, float z)
 {
     // y = vrsqrt14ps(z) for positive normal z
     const unsigned u = __float_as_uint(z);
     const unsigned e8 = (u >> 23) & 0xffu, m = u & 0x7fffffu;
     const unsigned par = (e8 & 1u) ^ 1u;
     const int k = ((int)e8 - 127 - (int)par) >> 1;
-    const uint2 c = trsq[(par << 6) | (m >> 17)];
-    const unsigned v = (c.x - c.y * ((m >> 8) & 0x1ffu)) >> 9;
+    const unsigned v = lut14(trsq, (par << 6) | (m >> 17), (m >> 8) & 0x1ffu);
     unsigned y = 0x3f000000u + (v << 7) - ((unsigned)k << 23);
     y = ((par | m) == 0u) ? ((unsigned)(127 - k) << 23) : y;
     float r = x86_rcp14_pos(trcp, __uint_as_float(y));          // y is a positive normal number
@@ -270,7 +288,7 @@ struct HashCtx {
     float qangle;            // IEEE: angles / PI;  X86: angles * (1 / PI)   (what g++ -ffast-math emits for Raisr.cpp:1553)
     int nangles;
     float quarter, half;     // X86 8-wide hash: Newton-refined rcpps(4), rcpps(2)
-    const uint2 *rsqrt14, *rcp14;          // shared-memory copies of the 14-bit instruction tables
+    const unsigned *rsqrt14, *rcp14;       // shared memory: packed, replicated 14-bit instruction tables, this lane's replica
     const uint16_t *rsqrtps, *rcpps;       // global (row tails only)
 };
 
@@ -528,11 +546,11 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     float *sQ = sGY + GR * QW;                                    // [RB][18][QW]
     unsigned char *sHash = smem_raw + OFF_HASH;                   // [HH][HP] bucket, 255 = not hashed
     unsigned char *sHash2 = smem_raw + OFF_HASH2;                 // [HH][OVW] 16-wide bucket of overlap columns, 255 = same
-    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + OFF_LUT);  // [0,128) rsqrt14, [128,256) rcp14
+    unsigned *sLut = reinterpret_cast<unsigned *>(smem_raw + OFF_LUT);  // packed + replicated rsqrt14, rcp14 (lut14_fill)
     void *mbar = smem_raw + OFF_MBAR;
 
     const int tid = threadIdx.x;
-    if (p.numerics != 0 && tid < 256) sLut[tid] = (tid < 128) ? p.lut_rsqrt14[tid] : p.lut_rcp14[tid - 128];
+    if (p.numerics != 0) lut14_fill(sLut, p.lut_rsqrt14, p.lut_rcp14, tid, NT);
     const int th = p.tile_h;
     const int x0 = blockIdx.x * TW;
     const int y0 = p.row0 + blockIdx.y * th;
@@ -589,7 +607,8 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     }
     __syncthreads();
 
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
+               p.lut_rsqrtps, p.lut_rcpps};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 
     for (int h0 = 0; h0 < hh; h0 += RB) {

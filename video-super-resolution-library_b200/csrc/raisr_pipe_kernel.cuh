@@ -53,7 +53,7 @@ constexpr size_t POFF_F = (POFF_HR + sizeof(float) * PHH * HP + 127) & ~(size_t)
 constexpr size_t POFF_HASH = POFF_F + sizeof(float) * SLICE_FLOATS;        // 2 bucket tiles
 constexpr size_t POFF_HASH2 = POFF_HASH + 2 * (size_t)PHH * HP;            // 2 overlap-column tiles
 constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)PHH * OVW + 15) & ~(size_t)15;
-constexpr size_t POFF_RING = POFF_LUT + 256 * sizeof(uint2);
+constexpr size_t POFF_RING = POFF_LUT + LUT_WORDS * sizeof(unsigned);
 constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;           // 2 chunks of column chains
 constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * 2 * QCHUNK;          // filter-slice mbarrier
 constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
@@ -350,14 +350,15 @@ template <typename PixT, int PT, int UPS, bool DEP>
 __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int tid)
 {
     const float (&gw)[6][6] = (sizeof(PixT) == 1) ? c_gw8 : c_gw10;
-    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
+    const unsigned *sLut = reinterpret_cast<const unsigned *>(smem_raw + POFF_LUT);
     float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
     float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
     const int th = p.tile_h, hh = th + 2;
     const int W = p.W, H = p.H;
     const int gx = (W + TW - 1) / TW;
     const int ntiles = pass_tiles(p);
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut, sLut + 128, p.lut_rsqrtps, p.lut_rcpps};
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
+               p.lut_rsqrtps, p.lut_rcpps};
 
     // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
     // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
@@ -826,11 +827,11 @@ template <typename PixT, int PT, int UPSA, int UPSB, bool F16>
 __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_constant__ PassParams pa, const __grid_constant__ PassParams pb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2 *sLut = reinterpret_cast<uint2 *>(smem_raw + POFF_LUT);
+    unsigned *sLut = reinterpret_cast<unsigned *>(smem_raw + POFF_LUT);
     unsigned long long *mslice = reinterpret_cast<unsigned long long *>(smem_raw + POFF_MBAR);
     const int tid0 = threadIdx.x;
 
-    if (pa.numerics != 0 && tid0 < 256) sLut[tid0] = (tid0 < 128) ? pa.lut_rsqrt14[tid0] : pa.lut_rcp14[tid0 - 128];
+    if (pa.numerics != 0) lut14_fill(sLut, pa.lut_rsqrt14, pa.lut_rcp14, tid0, NTP);
     for (int i = tid0; i < 2 * PHH * (HP - HW); i += NTP)                 // pad columns of both bucket tiles: "not hashed"
         smem_raw[POFF_HASH + (size_t)(i / (HP - HW)) * HP + HW + i % (HP - HW)] = 255;
     if (tid0 == 0) {
