@@ -26,10 +26,13 @@ enum {
     RAISR_NUMERICS_IEEE = 0,   /* sqrt.rn / div.rn: the specification in oracle/raisr_oracle.c (ORACLE_SQRT_IEEE)          */
     RAISR_NUMERICS_X86  = 1,   /* reproduces the compiled reference: vrcp14ps(vrsqrt14ps(x)) etc. via lookup tables          */
     RAISR_NUMERICS_X86_IF_AVAILABLE = 2, /* X86 when the tables are linked in, else IEEE (what RNLHandler_Init asks for)     */
-    RAISR_NUMERICS_FP16_FILTER = 3       /* OPT-IN fast numerics: hash as in mode 2 (buckets identical to the fp32 path), the 121-tap
+    RAISR_NUMERICS_FP16_FILTER = 3,      /* OPT-IN fast numerics: hash as in mode 2 (buckets identical to the fp32 path), the 121-tap
                                             filter in half precision (coefficients rounded to binary16, HMUL2/HFMA2 chains, fp32 tree);
                                             the counterpart of the reference's asm=avx512fp16 (Raisr_AVX512FP16.cpp:227-242).  8/10 bit
                                             only.  Y is NOT bit-identical to the fp32 path: see DESIGN.md for the measured error.       */
+    RAISR_NUMERICS_FAST_HASH = 4         /* OPT-IN experiment: the 11x11 Gaussian structure tensor as two 11-tap passes (the reference's
+                                            table is rank one up to 2e-6); hash numerics as in mode 2 behind it.  Buckets are NOT
+                                            bit-identical (measured agreement in DESIGN.md); filter and blend are the exact ones.        */
 };
 
 /* special values of raisr_cuda_config.device */

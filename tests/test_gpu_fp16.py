@@ -1,6 +1,6 @@
 """Opt-in fp16 filter stage (RAISR_NUMERICS_FP16_FILTER = 3): the counterpart of the reference's asm=avx512fp16
 (Raisr_AVX512FP16.cpp:227-242) on top of the EXACT fp32 hash.  Not bit-identical by design; what is promised -- and asserted here --
-is the error bound published in DESIGN.md section 2 (measured on full frames with tools/fp16_report.py):
+is the error bound published in DESIGN.md section 2 (measured on full frames with tools/numerics_report.py):
 
   * pass-1 buckets identical to the fp32 path (the hash does not change);
   * 8 bit, one pass : >= 99.5 % of the pixels within +-1 LSB of the fp32 path, mean |dY| <= 0.12 LSB;
@@ -65,3 +65,30 @@ def test_fp16_filter_stage_error_bound(folder, ratio, bits, passes, mode, size, 
 def test_fp16_filter_stage_is_rejected_for_16_bit_samples():
     with pytest.raises(RuntimeError):
         B.Engine(T.filter_folder("filters_2x/filters_lowres"), 2.0, 16, T.VideoRange, 1, 1, numerics=B.NUMERICS_FP16_FILTER)
+
+
+# ---- opt-in separable fast hash (RAISR_NUMERICS_FAST_HASH = 4): the experiment SURVEY section 7 (hard part 3) asks for -------------
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size", [
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (960, 540)),
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (960, 540)),
+    ("filters_1.5x/filters_highres", 1.5, 8, 1, 1, (640, 360)),
+])
+def test_separable_fast_hash_bucket_agreement(folder, ratio, bits, passes, mode, size):
+    """The Gaussian of the structure tensor as two 11-tap passes: other roundings, so buckets may flip at quantisation boundaries.
+    The bar: at least the reference's own AVX2 <-> AVX-512 agreement, 99.5 % of the buckets; pixels whose bucket
+    agrees are bit-identical (filter and blend are the exact ones)."""
+    w, h = size
+    img = T.synth_frame(w, h, bits, seed=4242)
+    y0, b0 = run(folder, img, ratio, bits, passes, mode, B.NUMERICS_AUTO)
+    y1, b1 = run(folder, img, ratio, bits, passes, mode, B.NUMERICS_FAST_HASH)
+    agree = 100.0 * (b0 == b1).mean()
+    assert agree >= 99.5, "pass-1 bucket agreement %.3f %%" % agree
+    assert ((b0 == -1) == (b1 == -1)).all(), "the set of hashed pixels must not change"
+    if passes == 1:
+        same = (b0 == b1) & (b0 >= 0)
+        # a pixel's value depends on its own bucket and, through the census blend, on its 8 neighbours' filtered values
+        import scipy.ndimage as ndi
+        clean = ndi.minimum_filter(same.astype(np.uint8), size=3) == 1
+        assert np.array_equal(y0[clean], y1[clean]), "pixels whose 3x3 neighbourhood kept its buckets must be bit-identical"
+    d = np.abs(y0.astype(np.int64) - y1.astype(np.int64))
+    assert 100.0 * (d == 0).mean() >= 99.0, "only %.2f %% of the pixels unchanged" % (100.0 * (d == 0).mean())

@@ -242,3 +242,34 @@ def test_pageable_planes_with_padded_steps_through_the_staging_pipeline(env, mon
     for b, o in zip(outb, outs):
         assert (b[:, o.shape[1]:] == 0xA5).all(), "bytes beyond the row width were written"
     eng.close()
+
+
+def test_lost_copy_flag_times_out_and_the_engine_recovers(monkeypatch, capfd):
+    """The kernel waits in-kernel for the flag behind the late input copy.  If that flag never comes (a failed copy; a profiler that
+    serialises the GPU so that the copy cannot run under the kernel) the wait gives up after ~2 s, the frame is re-run in plain
+    stream order and the engine stays there: the caller gets the right frame and a warning, never a hung device."""
+    import time
+    cfg = CONFIGS[0]
+    folder, ratio, bits, passes, mode, (w, h) = cfg
+    src = planes(w, h, bits, seed=88)
+    want = run_host(cfg, src, pinned=True)
+    monkeypatch.setenv("RAISR_CUDA_TEST_DROP_IN_FLAG", "1")
+    eng = B.Engine(T.filter_folder(folder), ratio, bits, T.VideoRange, passes, mode, numerics=B.NUMERICS_AUTO)
+    eng.set_res(w, h, 2 * w, 2 * h, w // 2, h // 2, w, h)
+    keep = []
+    ins = [_pin(a, keep) for a in src]
+    outs = [_pin(np.zeros((2 * h, 2 * w), np.uint8), keep), _pin(np.zeros((h, w), np.uint8), keep), _pin(np.zeros((h, w), np.uint8), keep)]
+    t0 = time.perf_counter()
+    assert eng.process_host(ins[0], outs[0], ins[1], ins[2], outs[1], outs[2]) == 0
+    first = time.perf_counter() - t0
+    for a, b, n in zip(want, outs, "YUV"):
+        assert np.array_equal(a, b), "%s plane differs after the recovery" % n
+    assert 1.5 < first < 10.0, "the first frame should have run into the ~2 s bound (took %.2f s)" % first
+    t0 = time.perf_counter()
+    for _ in range(5):
+        assert eng.process_host(ins[0], outs[0], ins[1], ins[2], outs[1], outs[2]) == 0
+    assert (time.perf_counter() - t0) / 5 < 0.05
+    for a, b, n in zip(want, outs, "YUV"):
+        assert np.array_equal(a, b)
+    eng.close()
+    assert "plain stream order" in capfd.readouterr().out

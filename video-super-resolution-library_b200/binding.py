@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libraisr.so")
 
-NUMERICS_IEEE, NUMERICS_X86, NUMERICS_AUTO, NUMERICS_FP16_FILTER = 0, 1, 2, 3
+NUMERICS_IEEE, NUMERICS_X86, NUMERICS_AUTO, NUMERICS_FP16_FILTER, NUMERICS_FAST_HASH = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):

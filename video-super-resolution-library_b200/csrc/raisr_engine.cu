@@ -204,6 +204,8 @@ struct raisr_cuda_engine {
     bool band_pipeline = true;      // luma D2H in row bands under the kernel; RAISR_CUDA_NO_BAND_PIPELINE=1 disables
     bool use_pipe = true;           // persistent warp-specialised kernel; RAISR_CUDA_KERNEL=tile selects the phase-sequential kernel (cross-check)
     float gw[11][6] = {};           // folded Gaussian weights of this engine's bit depth (copied into every launch's parameters)
+    bool test_drop_in_flag = false; // RAISR_CUDA_TEST_DROP_IN_FLAG=1 (tests only): drop the split-H2D flag of the first frame
+    bool fast_hash = false;         // RAISR_NUMERICS_FAST_HASH: separable structure tensor (opt-in, buckets not bit-identical)
     bool filter_fp16 = false;       // RAISR_NUMERICS_FP16_FILTER: half-precision filter stage (opt-in, Y not bit-identical); the hash keeps cfg.numerics
     bool chain_passes = true;       // two-pass configurations in one persistent launch; RAISR_CUDA_CHAIN=0: one launch per pass
     bool coop_launch = false;       // device supports cooperative launches (needed by the chained launch)
@@ -331,8 +333,9 @@ int cuda_failed(int err, const char *what)
 
 int launch_frame(raisr_cuda_engine *e, const FrameLaunch &fl)
 {
-    if (e->bps == 1) return e->filter_fp16 ? launch_frame_pipe<uint8_t, true>(fl) : launch_frame_pipe<uint8_t, false>(fl);
-    return e->filter_fp16 ? launch_frame_pipe<uint16_t, true>(fl) : launch_frame_pipe<uint16_t, false>(fl);
+    const int nv = e->filter_fp16 ? 1 : e->fast_hash ? 2 : 0;
+    if (e->bps == 1) return nv == 1 ? launch_frame_pipe<uint8_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint8_t, 2>(fl) : launch_frame_pipe<uint8_t, 0>(fl);
+    return nv == 1 ? launch_frame_pipe<uint16_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint16_t, 2>(fl) : launch_frame_pipe<uint16_t, 0>(fl);
 }
 
 // one pass = one launch
@@ -591,12 +594,22 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     // pipelined kernel reads its Gaussian weights from immutable constant tables that exist for 8 and 10 bit (raisr_gw_tables.h)
     if (cfg->bit_depth == 16) e->use_pipe = false;
     if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0;
+    if (const char *c = std::getenv("RAISR_CUDA_TEST_DROP_IN_FLAG")) e->test_drop_in_flag = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));
     {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
         e->coop_launch = coop != 0;
+    }
+    if (e->cfg.numerics == RAISR_NUMERICS_FAST_HASH) {
+        // opt-in fast numerics: separable structure tensor in front of the same eigen-analysis / quantisation
+        if (cfg->bit_depth > 10 || !e->use_pipe) {
+            std::cout << "[RAISR ERROR] the separable fast hash exists in the pipelined kernel (8 and 10 bit) only" << std::endl;
+            return fail(RNLErrorBadParameter);
+        }
+        e->fast_hash = true;
+        e->cfg.numerics = RAISR_NUMERICS_X86_IF_AVAILABLE;
     }
     if (e->cfg.numerics == RAISR_NUMERICS_FP16_FILTER) {
         // opt-in fast numerics: fp16 filter stage on top of the exact fp32 hash (buckets stay those of the fp32 path)
@@ -674,8 +687,9 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         // > 48 KB dynamic shared memory is a per-device function attribute: set for this engine's kernels on this engine's device
         int err = e->bps == 1 ? prepare_pass_tile<uint8_t>() : prepare_pass_tile<uint16_t>();
         if (!err) {
-            if (e->bps == 1) err = e->filter_fp16 ? prepare_frame_pipe<uint8_t, true>() : prepare_frame_pipe<uint8_t, false>();
-            else err = e->filter_fp16 ? prepare_frame_pipe<uint16_t, true>() : prepare_frame_pipe<uint16_t, false>();
+            const int nv = e->filter_fp16 ? 1 : e->fast_hash ? 2 : 0;
+            if (e->bps == 1) err = nv == 1 ? prepare_frame_pipe<uint8_t, 1>() : nv == 2 ? prepare_frame_pipe<uint8_t, 2>() : prepare_frame_pipe<uint8_t, 0>();
+            else err = nv == 1 ? prepare_frame_pipe<uint16_t, 1>() : nv == 2 ? prepare_frame_pipe<uint16_t, 2>() : prepare_frame_pipe<uint16_t, 0>();
         }
         if (err) { cuda_failed(err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); return fail(RNLErrorInsufficientResources); }
     }
@@ -972,7 +986,10 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
             CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
                                       static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
                                       cudaMemcpyHostToDevice, e->stream_h2d));
-            if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
+            // (test hook RAISR_CUDA_TEST_DROP_IN_FLAG=1: the first frame's flag is never written -- what a failed copy looks like to
+            //  the kernel; exercises the bounded spin, the error word and the fall-back to plain stream order)
+            if (e->test_drop_in_flag) e->test_drop_in_flag = false;
+            else if (e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, e->frame_seq, 0) != 0) return memop_failed("cuStreamWriteValue32");
             if (chroma) CUDA_OK(cudaEventRecord(e->ev_in, e->stream_h2d));  // the chroma copies queue up behind the luma copies
         } else if (chroma) {
             CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
@@ -1171,7 +1188,11 @@ int raisr_cuda_read_hash(raisr_cuda_engine *e, int pass, int32_t *host_out, size
 
 unsigned long long raisr_cuda_launch_count(const raisr_cuda_engine *e) { return e ? e->launches : 0; }
 
-int raisr_cuda_numerics(const raisr_cuda_engine *e) { return e ? (e->filter_fp16 ? (int)RAISR_NUMERICS_FP16_FILTER : e->cfg.numerics) : -1; }
+int raisr_cuda_numerics(const raisr_cuda_engine *e)
+{
+    if (!e) return -1;
+    return e->filter_fp16 ? (int)RAISR_NUMERICS_FP16_FILTER : e->fast_hash ? (int)RAISR_NUMERICS_FAST_HASH : e->cfg.numerics;
+}
 
 void raisr_cuda_destroy(raisr_cuda_engine *e)
 {

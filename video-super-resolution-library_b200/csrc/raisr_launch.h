@@ -17,9 +17,10 @@ struct FrameLaunch {
 };
 
 // cudaError_t as int; cudaErrorInvalidDeviceFunction = "no chained instantiation for this combination": launch the passes separately
-template <typename PixT, bool F16> int launch_frame_pipe(const FrameLaunch &fl);
+// NV: numerics variant (0 exact, 1 fp16 filter stage, 2 separable fast hash)
+template <typename PixT, int NV> int launch_frame_pipe(const FrameLaunch &fl);
 // per-device opt-in to > 48 KB dynamic shared memory for every instantiation of that translation unit (call once per engine)
-template <typename PixT, bool F16> int prepare_frame_pipe();
+template <typename PixT, int NV> int prepare_frame_pipe();
 
 template <typename PixT> int launch_pass_tile(const PassParams &p, int ups, dim3 grid, cudaStream_t s);
 template <typename PixT> int prepare_pass_tile();

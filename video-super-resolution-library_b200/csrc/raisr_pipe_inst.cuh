@@ -5,10 +5,10 @@
 
 namespace raisr {
 
-template <typename PixT, int PT, int UA, int UB, bool F16>
+template <typename PixT, int PT, int UA, int UB, int NV>
 static int launch_one(const FrameLaunch &fl)
 {
-    auto kern = raisr_frame_pipe_kernel<PixT, PT, UA, UB, F16>;
+    auto kern = raisr_frame_pipe_kernel<PixT, PT, UA, UB, NV>;
     if (UB < 0) {
         kern<<<fl.grid, NTP, PIPE_SMEM_BYTES, fl.stream>>>(fl.a, fl.a);
         return (int)cudaGetLastError();
@@ -18,10 +18,10 @@ static int launch_one(const FrameLaunch &fl)
     return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(fl.grid), dim3(NTP), args, PIPE_SMEM_BYTES, fl.stream);
 }
 
-template <typename PixT, int PT, int UA, int UB, bool F16>
+template <typename PixT, int PT, int UA, int UB, int NV>
 static int prepare_one()
 {
-    return (int)cudaFuncSetAttribute(raisr_frame_pipe_kernel<PixT, PT, UA, UB, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES);
+    return (int)cudaFuncSetAttribute(raisr_frame_pipe_kernel<PixT, PT, UA, UB, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM_BYTES);
 }
 
 // instantiated combinations: every single pass; chained pairs as the reference's two-pass modes produce them
@@ -30,21 +30,21 @@ static int prepare_one()
     X(4, 0, -1) X(4, 1, -1) X(4, 2, -1) X(1, 0, -1) X(1, 1, -1) X(1, 2, -1)                                              \
     X(4, 1, 0) X(4, 0, 1) X(1, 2, 0) X(1, 0, 2)
 
-template <typename PixT, bool F16>
+template <typename PixT, int NV>
 int launch_frame_pipe(const FrameLaunch &fl)
 {
     const int pt = fl.a.ptypes, ua = fl.ups_a, ub = fl.two ? fl.ups_b : -1;
-#define X(PT, UA, UB) if (pt == PT && ua == UA && ub == UB) return launch_one<PixT, PT, UA, UB, F16>(fl);
+#define X(PT, UA, UB) if (pt == PT && ua == UA && ub == UB) return launch_one<PixT, PT, UA, UB, NV>(fl);
     RAISR_PIPE_COMBOS(X)
 #undef X
     return (int)cudaErrorInvalidDeviceFunction;
 }
 
-template <typename PixT, bool F16>
+template <typename PixT, int NV>
 int prepare_frame_pipe()
 {
     int rc = 0;
-#define X(PT, UA, UB) if (!rc) rc = prepare_one<PixT, PT, UA, UB, F16>();
+#define X(PT, UA, UB) if (!rc) rc = prepare_one<PixT, PT, UA, UB, NV>();
     RAISR_PIPE_COMBOS(X)
 #undef X
     return rc;

@@ -60,10 +60,16 @@ constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(((PTH_MAX + 14) / 2 + 1) * LRP <= PHH * HP, "low-res staging fits in the HR tile");
 
-__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// (barrier number and thread count are IMMEDIATES: the count is part of the instruction, which is also what lets
+// compute-sanitizer's synccheck see that these are partial barriers and not a __syncthreads() some threads skip)
+template <int ID, int COUNT> __device__ __forceinline__ void group_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+#define group_sync(id, count) group_sync_c<(id), (count)>()
+// barrier pair selected by the bucket-tile buffer (0 / 1)
+template <int ID, int COUNT> __device__ __forceinline__ void group_sync_buf(int buf) { if (buf) group_sync_c<ID + 1, COUNT>(); else group_sync_c<ID, COUNT>(); }
 // producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
 // mbarrier spin), the signalling side does not wait (bar.arrive).  count = all threads of both sides.
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void named_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void named_arrive_buf(int buf) { if (buf) named_arrive_c<ID + 1, COUNT>(); else named_arrive_c<ID, COUNT>(); }
 constexpr int BAR_PROD = 1, BAR_CONS = 2, BAR_FULL = 3, BAR_EMPTY = 5, BAR_CHAIN = 7;   // FULL/EMPTY + bucket tile index (0/1)
 
 // Packed fp32 pairs (sm_100 FMUL2 / FFMA2): two IEEE round-to-nearest operations per instruction, i.e. the same roundings as
@@ -188,10 +194,22 @@ __device__ __forceinline__ void spin_wait_flag_geq(const unsigned *flag, unsigne
 // Split H2D: the lower part of the input plane (rows >= in_split_row) may still be on its way (own stream, flagged).  Called by
 // a warp group (its leader spins, the group's named barrier publishes the result) before the first access to such rows.  Not inlined, scalar arguments only (taking the
 // address of the kernel parameter block would move every access to it into local memory).
-static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader, int bar, int count)
+// The chunk hand-off of the two producer roles.  The chain warps and the bucket warps reach this named barrier from two different
+// places of the code: legal (the .aligned rule of bar.sync is per warp), but compute-sanitizer's synccheck expects the participants
+// of a barrier to meet at ONE instruction and reports "divergent threads".  -DRAISR_SYNCCHECK_BUILD routes both roles through a
+// single out-of-line barrier instruction (synccheck: 0 errors, profiles/r2_sanitizer.txt); the call costs 2.5 % (0.6054 vs
+// 0.5904 ms per 4K frame), so the shipped build keeps the barrier inline.
+#ifdef RAISR_SYNCCHECK_BUILD
+static __device__ __noinline__ void producer_chunk_barrier() { group_sync_c<BAR_PROD, NPT>(); }
+#else
+static __device__ __forceinline__ void producer_chunk_barrier() { group_sync_c<BAR_PROD, NPT>(); }
+#endif
+
+template <int BAR, int COUNT>
+static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader)
 {
     if (leader) spin_wait_flag(flag, seq, err);
-    group_sync(bar, count);
+    group_sync_c<BAR, COUNT>();
 }
 
 // Chroma planes: plain cheap upscale (Raisr.cpp:1373-1388) of this CTA's share of the planes, slice sl of nslices, by the filter
@@ -333,11 +351,12 @@ __device__ __forceinline__ void tile_input_rows(const PassParams &p, int y0, int
 // tiles per tile row (dep_done, zeroed by the host before the launch); before a group reads input rows [lo, hi] its leader waits
 // until every tile row of pass A that covers them is complete (bounded spin, ld.acquire.gpu: also drops stale L1 lines), the
 // group's named barrier publishes that.  `known` = tile rows [0, known) already seen complete (tiles come in row order).
-static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigned need, int ty_hi, int known, unsigned *err, bool leader, int bar, int count)
+template <int BAR, int COUNT>
+static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigned need, int ty_hi, int known, unsigned *err, bool leader)
 {
     if (leader)
         for (int ty = known; ty <= ty_hi; ++ty) spin_wait_flag_geq(done + ty, need, err);
-    group_sync(bar, count);
+    group_sync_c<BAR, COUNT>();
 }
 
 // =========================== producers: buckets of tile i -> bucket tile [i & 1] ===========================
@@ -346,10 +365,15 @@ static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigne
 // samples run on the phase-sequential kernel): compile-time constant-bank addresses, i.e. uniform operands of FMUL2 in both inlined
 // copies of this function.  (Read from the parameter block, the second copy of a chained launch staged all 66 weights through
 // registers and spilled them inside the column-chain loop: 1.50 ms instead of 1.21 ms for the two passes at 1080p->4K.)
-template <typename PixT, int PT, int UPS, bool DEP>
+// FASTH: opt-in separable "fast hash" (RAISR_NUMERICS_FAST_HASH).  The reference's 2-D Gaussian is rank one up to the 6 printed digits
+// of its literals (|w[i][k] - a[i] a[k]| <= 2.3e-6 w[i][k], a[i] = sqrt(w[i][i])), so GTWG = sum_i sum_k w[i][k] g g can run as an
+// 11-tap vertical pass (stage B: 3 values per position instead of 18 chains) and an 11-tap horizontal pass (stage C).  ~70 instead
+// of ~230 flops per pixel -- and other roundings: buckets are no longer bit-identical to the reference (measured agreement: DESIGN.md).
+template <typename PixT, int PT, int UPS, bool DEP, bool FASTH>
 __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int tid)
 {
     const float (&gw)[6][6] = (sizeof(PixT) == 1) ? c_gw8 : c_gw10;
+    const float (&ga)[6] = (sizeof(PixT) == 1) ? c_ga8 : c_ga10;
     const unsigned *sLut = reinterpret_cast<const unsigned *>(smem_raw + POFF_LUT);
     float *sRing = reinterpret_cast<float *>(smem_raw + POFF_RING);
     float *sQ = reinterpret_cast<float *>(smem_raw + POFF_Q);
@@ -401,6 +425,30 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
         // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
         auto stage_B = [&](int kb) {
             const int s0 = RBP * kb + rl;                            // S row above the first gradient row
+            if (FASTH) {
+                // vertical pass of the separable form: V_k3(r, x) = sum_i a[i] (g1 g2)(r + i, x)
+                f32x2 accA = 0ull;                                   // (xx, xy)
+                float accY = 0.0f;                                   // yy
+                float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
+                const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
+                float vcur = row[1];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
+                    const float vnext = nrow[1];
+                    const float gxv = fsub(vnext, vprev), gyv = fsub(row[2], row[0]);
+                    const float a = ga[i < 6 ? i : 10 - i];
+                    const float ax = fmul(a, gxv), ay = fmul(a, gyv);
+                    accA = fma2(pack2(ax, ax), pack2(gxv, gyv), accA);
+                    accY = ffma(ay, gyv, accY);
+                    vprev = vcur; vcur = vnext; row = nrow;
+                }
+                float *qd = sQ + ((gk + kb) & 1u) * QCHUNK + (rl * 18) * QW + q;
+                float xx, xy;
+                unpack2(accA, xx, xy);
+                qd[0] = xx; qd[QW] = xy; qd[2 * QW] = accY;
+                return;
+            }
             f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
@@ -445,13 +493,20 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
             const float *qs = sQ + ((gk + kc) & 1u) * QCHUNK + (rl * 18) * QW + j;
 #pragma unroll
             for (int k3 = 0; k3 < 3; ++k3) {
-                float lane[11];
+                if (FASTH) {                                         // horizontal pass: sum_k a[k] V_k3(r, c + k)
+                    float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    const int m = k < 6 ? k : 10 - k;
-                    lane[k] = qs[(m * 3 + k3) * QW + k];
+                    for (int k = 0; k < 11; ++k) acc = ffma(ga[k < 6 ? k : 10 - k], qs[k3 * QW + k], acc);
+                    g[k3] = acc;
+                } else {
+                    float lane[11];
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) {
+                        const int m = k < 6 ? k : 10 - k;
+                        lane[k] = qs[(m * 3 + k3) * QW + k];
+                    }
+                    g[k3] = tree_sum(lane);
                 }
-                g[k3] = tree_sum(lane);
             }
             const bool hashed = r >= 6 && r < H - 6 && c >= 6 && c < p.c_end;
             int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
@@ -475,7 +530,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                 int in_lo, in_last;
                 tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
                 if (in_last >= p.in_split_row) {
-                    wait_split_input(p.in_ready, p.in_seq, p.err_flag, lt == 0, BAR_CHAIN, NBT);
+                    wait_split_input<BAR_CHAIN, NBT>(p.in_ready, p.in_seq, p.err_flag, lt == 0);
                     input_complete = true;
                 }
             }
@@ -488,7 +543,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
 #else
                 if (ty_hi >= dep_known) {
 #endif
-                    wait_rows_done(p.dep_done, (unsigned)p.dep_gx, ty_hi, dep_known, p.err_flag, lt == 0, BAR_CHAIN, NBT);
+                    wait_rows_done<BAR_CHAIN, NBT>(p.dep_done, (unsigned)p.dep_gx, ty_hi, dep_known, p.err_flag, lt == 0);
                     dep_known = ty_hi + 1;
                 }
             }
@@ -526,15 +581,15 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                         }
                     }
                 }
-                group_sync(BAR_PROD, NPT);                               // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
+                producer_chunk_barrier();                                // B(k) published; C(k-1) is done with the other chain buffer; ring rows of chunk k+1 in place
             }
         } else {
-            if (cy.iter >= 2) group_sync(BAR_EMPTY + buf, NBT + NCT);    // the filter warps are done with this bucket tile (two tiles ago)
+            if (cy.iter >= 2) group_sync_buf<BAR_EMPTY, NBT + NCT>(buf);    // the filter warps are done with this bucket tile (two tiles ago)
             for (int k = 0; k < nchunks; ++k) {
-                group_sync(BAR_PROD, NPT);                               // B(k) is complete
+                producer_chunk_barrier();                                // B(k) is complete
                 stage_C(k);
             }
-            named_arrive(BAR_FULL + buf, NBT + NCT);                     // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
+            named_arrive_buf<BAR_FULL, NBT + NCT>(buf);                     // bucket tile [buf] is complete (bar.arrive orders this thread's writes)
         }
         cy.gk += (unsigned)nchunks;
     }
@@ -618,7 +673,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
         bool full_taken = false;
 #ifndef RAISR_EXP_NO_EARLY_FULL
         if (DEP) {
-            group_sync(BAR_FULL + buf, NBT + NCT);
+            group_sync_buf<BAR_FULL, NBT + NCT>(buf);
             full_taken = true;
         } else
 #endif
@@ -626,7 +681,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             int in_lo, in_last;
             tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
             if (in_last >= p.in_split_row) {
-                group_sync(BAR_FULL + buf, NBT + NCT);
+                group_sync_buf<BAR_FULL, NBT + NCT>(buf);
                 full_taken = input_complete = true;
             }
         }
@@ -672,7 +727,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
         }
         if (p.chroma_n > 0 && local_iter >= 2 && slices_done < nslices) chroma_slice(slices_done++);
         group_sync(BAR_CONS, NCT);                                        // S / HR tile complete
-        if (!full_taken) group_sync(BAR_FULL + buf, NBT + NCT);           // buckets of this tile are ready
+        if (!full_taken) group_sync_buf<BAR_FULL, NBT + NCT>(buf);           // buckets of this tile are ready
 
         // ---- D: 121-tap filter, one pixel type at a time ----
         const bool has_ov = (x0 - 1 + HW > p.tail_start) && (x0 - 1 < p.tail_start + OVW);
@@ -809,7 +864,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
         // ---- E: blend + store ----
         stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
         group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
-        if (cy.iter + 2 < cy.total_iters) named_arrive(BAR_EMPTY + buf, NBT + NCT);   // bucket tile may be refilled (two tiles on, possibly in the next pass)
+        if (cy.iter + 2 < cy.total_iters) named_arrive_buf<BAR_EMPTY, NBT + NCT>(buf);   // bucket tile may be refilled (two tiles on, possibly in the next pass)
         if (ct == 0 && (p.band_done || p.rows_done)) {
             __threadfence();                                              // the tile's stores (ordered before by the barrier) -> device scope
             if (p.band_done && !(p.out_tail && y0 >= p.tail_row0)) atomicAdd(p.band_done + ty / p.band_tiles_y, 1u);
@@ -823,7 +878,8 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
 // UPSA / UPSB: upscale flavour of the first / second pass of the launch (0 = none, 1 = exact 2x, 2 = axis maps); UPSB = -1: one
 // pass.  With two passes (pb.dep_done set by the host, cooperative launch: all CTAs resident) the second pass reads the plane
 // the first one writes; tile rows are handed over through pa.rows_done / pb.dep_done.
-template <typename PixT, int PT, int UPSA, int UPSB, bool F16>
+// NV: numerics variant of the launch -- 0: exact (bit-identical to the reference), 1: fp16 filter stage, 2: separable fast hash.
+template <typename PixT, int PT, int UPSA, int UPSB, int NV>
 __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_constant__ PassParams pa, const __grid_constant__ PassParams pb)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -855,12 +911,12 @@ __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_c
         // hand registers to the filter warpgroups; the chain warps (18 accumulators) need fewer than the hash
         if (tid >= NBT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BUCKET_REGS));
-        pipe_producer_pass<PixT, PT, UPSA, false>(pa, smem_raw, b, cy, tid);
-        if constexpr (UPSB >= 0) pipe_producer_pass<PixT, PT, UPSB, true>(pb, smem_raw, tileB0, cy, tid);
+        pipe_producer_pass<PixT, PT, UPSA, false, NV == 2>(pa, smem_raw, b, cy, tid);
+        if constexpr (UPSB >= 0) pipe_producer_pass<PixT, PT, UPSB, true, NV == 2>(pb, smem_raw, tileB0, cy, tid);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-        pipe_filter_pass<PixT, PT, UPSA, false, F16>(pa, smem_raw, b, cy, tid0);
-        if constexpr (UPSB >= 0) pipe_filter_pass<PixT, PT, UPSB, true, F16>(pb, smem_raw, tileB0, cy, tid0);
+        pipe_filter_pass<PixT, PT, UPSA, false, NV == 1>(pa, smem_raw, b, cy, tid0);
+        if constexpr (UPSB >= 0) pipe_filter_pass<PixT, PT, UPSB, true, NV == 1>(pb, smem_raw, tileB0, cy, tid0);
     }
 }
 

@@ -1,6 +1,6 @@
-// pipelined kernel, uint8_t samples, fp32 filter stage (bit-exact): see raisr_pipe_inst.cuh
+// pipelined kernel, uint8_t samples, exact: see raisr_pipe_inst.cuh
 #include "raisr_pipe_inst.cuh"
 namespace raisr {
-template int launch_frame_pipe<uint8_t, false>(const FrameLaunch &);
-template int prepare_frame_pipe<uint8_t, false>();
+template int launch_frame_pipe<uint8_t, 0>(const FrameLaunch &);
+template int prepare_frame_pipe<uint8_t, 0>();
 }  // namespace raisr

@@ -1,6 +1,6 @@
 // pipelined kernel, uint8_t samples, fp16 filter stage (opt-in numerics 3): see raisr_pipe_inst.cuh
 #include "raisr_pipe_inst.cuh"
 namespace raisr {
-template int launch_frame_pipe<uint8_t, true>(const FrameLaunch &);
-template int prepare_frame_pipe<uint8_t, true>();
+template int launch_frame_pipe<uint8_t, 1>(const FrameLaunch &);
+template int prepare_frame_pipe<uint8_t, 1>();
 }  // namespace raisr
