@@ -6,7 +6,8 @@
  * `evenoutput` (vf_raisr.c:217-221).  Frames never leave the GPU: NVDEC -> raisr_cuda -> NVENC.
  *
  *   ffmpeg -init_hw_device cuda=cu:0 -filter_hw_device cu -hwaccel cuda -hwaccel_output_format cuda -i in.mp4 \
- *          -vf "scale_cuda=format=yuv420p,raisr_cuda=ratio=2:filterfolder=/path/filters_2x/filters_lowres" -c:v hevc_nvenc out.mp4
+ *          -vf "raisr_cuda=ratio=2:filterfolder=/path/filters_2x/filters_lowres" -c:v hevc_nvenc out.mp4
+ * (NVDEC's nv12 / p010 frames are taken as they are; planar yuv420p/422p/444p frames too)
  *
  * Instead of the process-global RNLHandler_* engine this filter owns a raisr_cuda_engine (include/raisr_cuda.h), so several
  * filter instances (and devices) can live in one process.  The engine is created with device = RAISR_CUDA_DEVICE_CALLER_CONTEXT:
@@ -54,6 +55,7 @@ typedef struct RaisrCudaContext {
     AVBufferRef *frames_ctx;            /* output frames */
     enum AVPixelFormat sw_format;
     raisr_cuda_engine *engine;
+    int layout;                         /* 1 planar, 2 semi-planar (NV12 / P010) */
     int res_set;
 } RaisrCudaContext;
 
@@ -77,17 +79,23 @@ static av_cold void raisr_cuda_uninit(AVFilterContext *avctx)
     av_buffer_unref(&s->frames_ctx);
 }
 
-/* planar YUV, three planes, 8 bits in bytes or 10/16 bits in little-endian 16-bit words: what the engine's planes are */
-static int format_is_supported(const AVPixFmtDescriptor *desc, int bits)
+/* 1: planar YUV (three planes: yuv420p/422p/444p, 8 bits in bytes or 10 bits in little-endian 16-bit words);
+ * 2: semi-planar 4:2:0 (NV12, P010: U and V interleaved in plane 1, P010 with its value in the high bits) -- the formats of
+ *    vf_raisr_opencl.c:166-169; 0: not supported */
+static int format_layout(const AVPixFmtDescriptor *desc, int bits)
 {
     if (!desc || (desc->flags & (AV_PIX_FMT_FLAG_RGB | AV_PIX_FMT_FLAG_PAL | AV_PIX_FMT_FLAG_BITSTREAM | AV_PIX_FMT_FLAG_BE)))
         return 0;
-    if (!(desc->flags & AV_PIX_FMT_FLAG_PLANAR) || desc->nb_components != 3)
+    if (!(desc->flags & AV_PIX_FMT_FLAG_PLANAR) || desc->nb_components != 3 || desc->comp[0].depth != bits)
         return 0;
-    for (int c = 0; c < 3; c++)
-        if (desc->comp[c].plane != c || desc->comp[c].shift != 0 || desc->comp[c].depth != bits)
-            return 0;                   /* semi-planar NV12 / P010 (shared chroma plane, shifted samples): convert with scale_cuda first */
-    return 1;
+    if (desc->comp[0].plane == 0 && desc->comp[1].plane == 1 && desc->comp[2].plane == 2 &&
+        desc->comp[0].shift == 0 && desc->comp[1].shift == 0 && desc->comp[2].shift == 0)
+        return 1;
+    if (desc->comp[0].plane == 0 && desc->comp[1].plane == 1 && desc->comp[2].plane == 1 &&
+        desc->log2_chroma_w == 1 && desc->log2_chroma_h == 1 && desc->comp[1].offset < desc->comp[2].offset &&
+        desc->comp[1].shift == desc->comp[0].shift && desc->comp[2].shift == desc->comp[0].shift)
+        return 2;                       /* NV12 / P010 (U first); NV21 is not */
+    return 0;
 }
 
 static int raisr_cuda_config_output(AVFilterLink *outlink)
@@ -116,8 +124,9 @@ static int raisr_cuda_config_output(AVFilterLink *outlink)
         av_log(avctx, AV_LOG_ERROR, "input pixel doesn't match model's bitdepth\n");
         return AVERROR(EINVAL);
     }
-    if (!format_is_supported(desc, s->bits)) {
-        av_log(avctx, AV_LOG_ERROR, "unsupported sw format %s: planar yuv420p/422p/444p (8 bit) or their 10-bit LE forms\n",
+    s->layout = format_layout(desc, s->bits);
+    if (!s->layout) {
+        av_log(avctx, AV_LOG_ERROR, "unsupported sw format %s: nv12, p010, or planar yuv420p/422p/444p (8 bit / 10-bit LE)\n",
                av_get_pix_fmt_name(s->sw_format));
         return AVERROR(ENOSYS);
     }
@@ -217,10 +226,15 @@ static int raisr_cuda_filter_frame(AVFilterLink *inlink, AVFrame *in)
     }
     /* one launch per pass carries the whole frame (luma pass + both chroma resizes), asynchronous on FFmpeg's stream:
      * downstream CUDA consumers (NVENC, hwdownload) are ordered behind it on the same stream */
-    rc = raisr_cuda_process_device(s->engine,
-                                   in->data[0],  in->linesize[0],  in->data[1],  in->linesize[1],  in->data[2],  in->linesize[2],
-                                   out->data[0], out->linesize[0], out->data[1], out->linesize[1], out->data[2], out->linesize[2],
-                                   s->blending, s->hwctx->stream);
+    if (s->layout == 2)                                         /* NV12 / P010 straight from NVDEC, straight into NVENC */
+        rc = raisr_cuda_process_device_semiplanar(s->engine, in->data[0], in->linesize[0], in->data[1], in->linesize[1],
+                                                  out->data[0], out->linesize[0], out->data[1], out->linesize[1],
+                                                  desc->comp[0].shift, s->blending, s->hwctx->stream);
+    else
+        rc = raisr_cuda_process_device(s->engine,
+                                       in->data[0],  in->linesize[0],  in->data[1],  in->linesize[1],  in->data[2],  in->linesize[2],
+                                       out->data[0], out->linesize[0], out->data[1], out->linesize[1], out->data[2], out->linesize[2],
+                                       s->blending, s->hwctx->stream);
     CHECK_CU(cu->cuCtxPopCurrent(&dummy));
     if (rc != RNLErrorNone) {
         av_log(avctx, AV_LOG_ERROR, "raisr_cuda_process_device error (0x%08x)\n", (unsigned)rc);

@@ -76,6 +76,15 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
                               void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending,
                               void *stream);
 
+/* One frame with DEVICE planes in SEMI-PLANAR layout -- NV12 (8 bit) and P010 (16-bit words, 10-bit value in the high bits:
+ * sample_shift = 6), what NVDEC produces and NVENC consumes, and two of the three formats of the reference's hardware-frame filter
+ * (vf_raisr_opencl.c:166-169; its kernels apply VideoDataType.bitShift the same way, Raisr.cpp:1313-1348).  in_uv / out_uv hold U and V
+ * interleaved; chroma geometry as given to raisr_cuda_set_res (pairs per row = chroma width).  Samples are read as word >> sample_shift
+ * and written as value << sample_shift, luma and chroma alike.  Same single launch per frame as the planar entry. */
+int raisr_cuda_process_device_semiplanar(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_uv,
+                                         size_t in_uv_step, void *out_y, size_t out_y_step, void *out_uv, size_t out_uv_step,
+                                         int sample_shift, int blending, void *stream);
+
 /* Row-band form of the luma path for multi-GPU sharding (the reference's per-thread bands, Raisr.cpp:1738-1779):
  * computes output rows [row0, row1) only; in_y still points at row 0 of the full input plane, of which only
  * the rows the band depends on are read.  With two passes the first pass is recomputed on the rows the second can

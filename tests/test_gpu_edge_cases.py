@@ -160,3 +160,47 @@ def test_row_bands_reproduce_full_frame(folder, ratio, bits, passes, mode):
     got = d_out.cpu().numpy().view(img.dtype)
     eng.close()
     assert np.array_equal(got, full), "bands differ from the full frame on %d px" % (got != full).sum()
+
+
+@pytest.mark.parametrize("folder,ratio,bits,passes,mode,size,shift", [
+    ("filters_2x/filters_lowres", 2.0, 8, 1, 1, (640, 360), 0),            # NV12
+    ("filters_2x/filters_denoise", 2.0, 10, 2, 2, (640, 360), 6),          # P010: value in the high 10 bits, two passes chained
+    ("filters_1.5x/filters_highres", 1.5, 8, 1, 1, (426, 240), 0),         # NV12 at 1.5x: generic chroma path
+    ("filters_2x/filters_highres", 2.0, 10, 2, 1, (322, 182), 6),          # P010, odd chroma sizes: no vector stores
+], ids=["nv12", "p010-p2m2", "nv12-1.5x", "p010-odd"])
+def test_semiplanar_device_frames_equal_planar_frames(folder, ratio, bits, passes, mode, size, shift):
+    """NV12 / P010 device frames (what NVDEC and NVENC use; two of the three formats of vf_raisr_opencl.c:166-169) through
+    raisr_cuda_process_device_semiplanar == the planar result, sample for sample: interleaved chroma in, interleaved chroma out,
+    and for P010 every sample read as word >> 6 and written as value << 6."""
+    import torch
+    w, h = size
+    oW, oH = int(w * ratio), int(h * ratio)
+    cw, ch, ocw, och = (w + 1) // 2, (h + 1) // 2, (oW + 1) // 2, (oH + 1) // 2
+    dt = np.uint8 if bits == 8 else np.uint16
+    tdt = torch.uint8 if bits == 8 else torch.int16
+    y = T.synth_frame(w, h, bits, seed=321)
+    u, v = T.synth_chroma(cw, ch, bits, 5).astype(dt), T.synth_chroma(cw, ch, bits, 6).astype(dt)
+    f = T.filter_folder(folder)
+    # planar reference result through the host entry
+    eng = B.Engine(f, ratio, bits, T.VideoRange, passes, mode, numerics=NUM)
+    eng.set_res(w, h, oW, oH, cw, ch, ocw, och)
+    py, pu, pv = np.zeros((oH, oW), dt), np.zeros((och, ocw), dt), np.zeros((och, ocw), dt)
+    assert eng.process_host(y, py, u, v, pu, pv) == 0
+    # semi-planar device frames
+    uv = np.empty((ch, 2 * cw), dt)
+    uv[:, 0::2], uv[:, 1::2] = u, v
+    as_t = lambda a: torch.from_numpy((a.astype(np.uint32) << shift).astype(dt).view(np.int16) if bits != 8 else a).cuda()
+    d_y, d_uv = as_t(y), as_t(uv)
+    o_y = torch.zeros((oH, oW), dtype=tdt, device="cuda")
+    o_uv = torch.zeros((och, 2 * ocw), dtype=tdt, device="cuda")
+    bps = 1 if bits == 8 else 2
+    for _ in range(2):
+        assert eng.process_device_semiplanar(d_y.data_ptr(), d_y.stride(0) * bps, d_uv.data_ptr(), d_uv.stride(0) * bps,
+                                             o_y.data_ptr(), o_y.stride(0) * bps, o_uv.data_ptr(), o_uv.stride(0) * bps, shift) == 0
+    torch.cuda.synchronize()
+    gy, guv = o_y.cpu().numpy().view(dt), o_uv.cpu().numpy().view(dt)
+    eng.close()
+    if shift:
+        assert (gy & ((1 << shift) - 1)).max() == 0 and (guv & ((1 << shift) - 1)).max() == 0, "low bits must stay clear"
+    assert np.array_equal(gy >> shift, py), "Y differs on %d px" % ((gy >> shift) != py).sum()
+    assert np.array_equal(guv[:, 0::2] >> shift, pu) and np.array_equal(guv[:, 1::2] >> shift, pv), "chroma differs"

@@ -34,6 +34,8 @@ def lib():
         L.raisr_cuda_process_host.argtypes = [vp] + [vp, sz] * 6 + [C.c_int]
         L.raisr_cuda_process_device.restype = C.c_int32
         L.raisr_cuda_process_device.argtypes = [vp] + [vp, sz] * 6 + [C.c_int, vp]
+        L.raisr_cuda_process_device_semiplanar.restype = C.c_int32
+        L.raisr_cuda_process_device_semiplanar.argtypes = [vp] + [vp, sz] * 4 + [C.c_int, C.c_int, vp]
         L.raisr_cuda_process_device_rows.restype = C.c_int32
         L.raisr_cuda_process_device_rows.argtypes = [vp, vp, sz, vp, sz, C.c_int, C.c_uint, C.c_uint, vp]
         L.raisr_cuda_read_hash.restype = C.c_int32
@@ -110,6 +112,11 @@ class Engine:
         """raw device pointers (ints)"""
         return self.L.raisr_cuda_process_device(self.h, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y,
                                                 out_y_step, out_u, out_u_step, out_v, out_v_step, blending, stream)
+
+    def process_device_semiplanar(self, in_y, in_y_step, in_uv, in_uv_step, out_y, out_y_step, out_uv, out_uv_step, shift=0, blending=2, stream=None):
+        """NV12 (shift 0) / P010 (shift 6) device frames: raw device pointers (ints)"""
+        return self.L.raisr_cuda_process_device_semiplanar(self.h, in_y, in_y_step, in_uv, in_uv_step, out_y, out_y_step, out_uv, out_uv_step,
+                                                           shift, blending, stream)
 
     def process_device_rows(self, in_y, in_y_step, out_y, out_y_step, row0, row1, blending=2, stream=None):
         return self.L.raisr_cuda_process_device_rows(self.h, in_y, in_y_step, out_y, out_y_step, blending, row0, row1, stream)

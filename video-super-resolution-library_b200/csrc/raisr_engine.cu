@@ -198,6 +198,7 @@ struct raisr_cuda_engine {
     bool bind_device = true;        // false (cfg.device == RAISR_CUDA_DEVICE_CALLER_CONTEXT): run in whatever CUDA context the caller made current, never switch
     int num_sms = 148;
     int blending = 2;               // BlendingMode of the frame being processed
+    int sample_shift = 0;           // frame being processed: samples carry their value in the high bits (P010: 6); 0 for everything else
     bool no_memops = false;         // RAISR_CUDA_NO_MEMOPS=1 (or CUDA_LAUNCH_BLOCKING=1): no in-kernel flag waits, everything in plain stream order
     bool split_h2d = true;          // pipelined kernel: input plane in two copies, the second one under the kernel; RAISR_CUDA_SPLIT_H2D=0 disables
     bool tail_in_place = true;      // rows of the last round of tiles go straight into a page-locked output plane (no copy after the kernel); RAISR_CUDA_TAIL_IN_PLACE=0 disables
@@ -437,6 +438,7 @@ void set_upscale(const raisr_cuda_engine *e, PassParams *p)
 struct ChromaJob {
     const void *in[2]; size_t in_step[2];
     void *out[2]; size_t out_step[2];
+    int comps = 1;                             // 2: ONE semi-planar plane in in[0] / out[0] (U and V interleaved)
     const unsigned *ready; unsigned seq;       // optional H2D completion flag
     unsigned *done;                            // optional per-CTA completion counter
 };
@@ -444,7 +446,9 @@ struct ChromaJob {
 void set_chroma(const raisr_cuda_engine *e, const ChromaJob *c, PassParams *p)
 {
     if (!c) return;
-    p->chroma_n = 2;
+    p->chroma_n = c->comps == 2 ? 1 : 2;
+    p->c_comps = c->comps;
+    p->c_shift = e->sample_shift;
     for (int i = 0; i < 2; ++i) {
         p->chroma[i].in = c->in[i]; p->chroma[i].in_pitch = c->in_step[i];
         p->chroma[i].out = c->out[i]; p->chroma[i].out_pitch = c->out_step[i];
@@ -469,6 +473,7 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
         p.out = out_y; p.out_pitch = out_step; p.W = e->out_w; p.H = e->out_h; p.row0 = row0; p.row1 = row1;
         pass_common(e, 0, p.W, &p);
         set_upscale(e, &p);
+        p.in_shift = p.out_shift = e->sample_shift;
         p.band_done = band_done; p.out_tail = out_tail; p.out_tail_pitch = out_tail_step;
         p.in_ready = in_ready; p.in_seq = e->frame_seq; p.in_split_row = in_split_row;
         return launch_pass(e, p, s);
@@ -495,6 +500,8 @@ int run_luma(raisr_cuda_engine *e, const void *in_y, size_t in_step, void *out_y
     p2.out = out_y; p2.out_pitch = out_step; p2.W = e->out_w; p2.H = e->out_h; p2.row0 = row0; p2.row1 = row1;
     pass_common(e, 1, p2.W, &p2);
     if (mode2) set_upscale(e, &p2);
+    p1.in_shift = e->sample_shift;               // the intermediate plane holds plain values
+    p2.out_shift = e->sample_shift;
     p2.band_done = band_done; p2.out_tail = out_tail; p2.out_tail_pitch = out_tail_step;
     p1.in_ready = in_ready; p1.in_seq = e->frame_seq; p1.in_split_row = in_split_row;
     set_chroma(e, chroma, &p1);                  // resized while pass 1's filter warps finish
@@ -787,6 +794,7 @@ int raisr_cuda_process_device_rows(raisr_cuda_engine *e, const void *in_y, size_
     if (!e || !e->have_res || !in_y || !out_y || row0 >= row1 || row1 > (unsigned)e->out_h) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
     e->blending = blending;
+    e->sample_shift = 0;
     if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (unsigned i = 0; i < e->cfg.passes; ++i)
@@ -804,10 +812,13 @@ int raisr_cuda_process_device(raisr_cuda_engine *e, const void *in_y, size_t in_
         // one launch per pass: the chroma planes ride along with the (first) luma launch
         if (check_blending(blending)) return RNLErrorBadParameter;
         e->blending = blending;
+        e->sample_shift = 0;
         if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
         for (unsigned i = 0; i < e->cfg.passes; ++i)
             if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
-        const ChromaJob cj{{in_u, in_v}, {in_u_step, in_v_step}, {out_u, out_v}, {out_u_step, out_v_step}, nullptr, 0, nullptr};
+        ChromaJob cj{};
+        cj.in[0] = in_u; cj.in[1] = in_v; cj.in_step[0] = in_u_step; cj.in_step[1] = in_v_step;
+        cj.out[0] = out_u; cj.out[1] = out_v; cj.out_step[0] = out_u_step; cj.out_step[1] = out_v_step;
         return run_luma(e, in_y, in_y_step, out_y, out_y_step, 0, e->out_h, s, nullptr, nullptr, &cj);
     }
     int rc = raisr_cuda_process_device_rows(e, in_y, in_y_step, out_y, out_y_step, blending, 0, e->out_h, stream);
@@ -1104,6 +1115,32 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
 
 extern "C" {
 
+int raisr_cuda_process_device_semiplanar(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_uv, size_t in_uv_step,
+                                         void *out_y, size_t out_y_step, void *out_uv, size_t out_uv_step, int sample_shift, int blending,
+                                         void *stream)
+{
+    if (!e || !e->have_res || !in_y || !out_y || !in_uv || !out_uv) return RNLErrorBadParameter;
+    if (sample_shift < 0 || sample_shift > 8 || (e->bps == 1 && sample_shift != 0)) return RNLErrorBadParameter;
+    if (!e->use_pipe) {
+        std::cout << "[RAISR ERROR] semi-planar frames need the pipelined kernel" << std::endl;
+        return RNLErrorBadParameter;
+    }
+    if (check_blending(blending)) return RNLErrorBadParameter;
+    e->blending = blending;
+    e->sample_shift = sample_shift;
+    if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (unsigned i = 0; i < e->cfg.passes; ++i)
+        if (e->d_hash[i]) CUDA_OK(cudaMemsetAsync(e->d_hash[i], 0xff, sizeof(int) * (size_t)e->hash_w[i] * e->hash_h[i], s));
+    ChromaJob cj{};
+    cj.comps = 2;
+    cj.in[0] = in_uv; cj.in_step[0] = in_uv_step;
+    cj.out[0] = out_uv; cj.out_step[0] = out_uv_step;
+    const int rc = run_luma(e, in_y, in_y_step, out_y, out_y_step, 0, e->out_h, s, nullptr, nullptr, &cj);
+    e->sample_shift = 0;
+    return rc;
+}
+
 int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, const void *in_u,
                             size_t in_u_step, const void *in_v, size_t in_v_step, void *out_y, size_t out_y_step,
                             void *out_u, size_t out_u_step, void *out_v, size_t out_v_step, int blending)
@@ -1111,6 +1148,7 @@ int raisr_cuda_process_host(raisr_cuda_engine *e, const void *in_y, size_t in_y_
     if (!e || !e->have_res || !in_y || !out_y) return RNLErrorBadParameter;
     if (check_blending(blending)) return RNLErrorBadParameter;
     e->blending = blending;
+    e->sample_shift = 0;
     if (e->bind_device) CUDA_OK(cudaSetDevice(e->device));
     const bool chroma = in_u && in_v && out_u && out_v && e->d_in[1].ptr;
     int rc = e->use_pipe ? process_host_pipe(e, in_y, in_y_step, in_u, in_u_step, in_v, in_v_step, out_y, out_y_step, out_u, out_u_step, out_v, out_v_step, chroma)

@@ -33,6 +33,7 @@ struct PassParams {
     size_t out_pitch;        // bytes
     int W, H;
     int row0, row1;          // output rows this launch produces: [row0, row1)
+    int in_shift, out_shift; // samples carry their value in the HIGH bits (P010: 10 bits << 6): read as in >> in_shift, written as v << out_shift
     int upscale;             // 0: S = in,  1: S = resize(in)
     const int *xmap;         // [W] (i0 << 1 | step) : left source column, whether the right tap is i0+1
     const int *xw;           // [W] numerator of the right tap's weight over denx
@@ -77,6 +78,8 @@ struct PassParams {
     int c_in_w, c_in_h, c_W, c_H;
     const int *c_xmap, *c_xw, *c_ymap, *c_yw;
     int c_denx, c_deny;
+    int c_comps;                    // 1: planar chroma (chroma[0] = U, chroma[1] = V); 2: ONE semi-planar plane (NV12 / P010: U and V interleaved, chroma_n = 1)
+    int c_shift;                    // chroma samples: value in the high bits (P010: 6), applied on load and store
     const unsigned *chroma_ready;   // optional: set to chroma_seq once the planes' H2D copies have landed
     unsigned chroma_seq;
     unsigned *chroma_done;          // optional: incremented once per CTA when its share of the chroma planes is written
@@ -131,7 +134,7 @@ __device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool 
 {
     if (!upscale) {
         const PixT *row = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)Y * p.in_pitch);
-        return (float)row[X];
+        return (float)((unsigned)row[X] >> p.in_shift);
     }
     const int xm = __ldg(p.xmap + X), ym = __ldg(p.ymap + Y);
     const int x0 = xm >> 1, x1 = x0 + (xm & 1), y0 = ym >> 1, y1 = y0 + (ym & 1);
@@ -139,7 +142,7 @@ __device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool 
     const int wx0 = p.denx - wx1, wy0 = p.deny - wy1;
     const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)y0 * p.in_pitch);
     const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)y1 * p.in_pitch);
-    const unsigned a = ra[x0], b = ra[x1], c = rb[x0], d = rb[x1];
+    const unsigned a = (unsigned)ra[x0] >> p.in_shift, b = (unsigned)ra[x1] >> p.in_shift, c = (unsigned)rb[x0] >> p.in_shift, d = (unsigned)rb[x1] >> p.in_shift;
     const unsigned long long DD = (unsigned long long)p.denx * (unsigned long long)p.deny;
     if (DD * 65535ull < 0x7fffffffull) {      // small denominators (2x: 16, 1.5x: 36): 32-bit arithmetic
         const unsigned s = (unsigned)wy0 * ((unsigned)wx0 * a + (unsigned)wx1 * b) + (unsigned)wy1 * ((unsigned)wx0 * c + (unsigned)wx1 * d);
@@ -149,6 +152,25 @@ __device__ __forceinline__ float load_S(const PassParams &p, int Y, int X, bool 
     const unsigned long long s = (unsigned long long)wy0 * ((unsigned long long)wx0 * a + (unsigned long long)wx1 * b) +
                                  (unsigned long long)wy1 * ((unsigned long long)wx0 * c + (unsigned long long)wx1 * d);
     return (float)((s + DD / 2) / DD);
+}
+
+// the same sample for one component of a plane whose pixels are `comps` interleaved components (semi-planar chroma), value in the
+// high bits (>> shift); axis maps and denominators from p
+template <typename PixT>
+__device__ __forceinline__ unsigned bilinear_sample(const PassParams &p, const void *in, size_t in_pitch, int Y, int X, int comps, int cc, int shift)
+{
+    const int xm = __ldg(p.xmap + X), ym = __ldg(p.ymap + Y);
+    const int x0 = xm >> 1, x1 = x0 + (xm & 1), y0 = ym >> 1, y1 = y0 + (ym & 1);
+    const int wx1 = __ldg(p.xw + X), wy1 = __ldg(p.yw + Y);
+    const int wx0 = p.denx - wx1, wy0 = p.deny - wy1;
+    const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(in) + (size_t)y0 * in_pitch);
+    const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(in) + (size_t)y1 * in_pitch);
+    const unsigned long long a = (unsigned)ra[x0 * comps + cc] >> shift, b = (unsigned)ra[x1 * comps + cc] >> shift;
+    const unsigned long long c = (unsigned)rb[x0 * comps + cc] >> shift, d = (unsigned)rb[x1 * comps + cc] >> shift;
+    const unsigned long long DD = (unsigned long long)p.denx * (unsigned long long)p.deny;
+    const unsigned long long s = (unsigned long long)wy0 * ((unsigned long long)wx0 * a + (unsigned long long)wx1 * b) +
+                                 (unsigned long long)wy1 * ((unsigned long long)wx0 * c + (unsigned long long)wx1 * d);
+    return (unsigned)((s + DD / 2) / DD);
 }
 
 // ---- x86 approximation instructions via tables (numerics == X86) ------------------------------------
@@ -509,7 +531,7 @@ __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const f
                 r = (v < (float)p.lo) ? p.lo : ((v > (float)p.hi) ? p.hi : (int)v);
                 if (sHash[(ty + 1) * HP + tx + 1 + e] == 255) r = (int)lc;               // not hashed: border copy of the upscale
             }
-            iv[e] = r;
+            iv[e] = r << p.out_shift;
         }
         const bool tail = p.out_tail != nullptr && Y >= p.tail_row0;
         PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(tail ? p.out_tail : p.out) + (size_t)Y * (tail ? p.out_tail_pitch : p.out_pitch)) + X;
@@ -573,7 +595,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
         for (int idx = tid; idx < lrh * LRW; idx += NT) {
             const int ly = idx / LRW, lx = idx - ly * LRW;
             const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
-            sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
+            sL[ly * LRP + lx] = (float)((unsigned)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx] >> p.in_shift);
         }
         __syncthreads();
         // block (bi,bj) centred on low-res (bi,bj) emits S rows 2bi-1, 2bi and cols 2bj-1, 2bj (tile-local)

@@ -135,7 +135,7 @@ __device__ __forceinline__ float sample_S(const PassParams &p, int Y, int X)
         const int xa = min(max((X & 1) ? jx : jx - 1, 0), p.in_w - 1), xb = min(max((X & 1) ? jx + 1 : jx, 0), p.in_w - 1);
         const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
         const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
-        const float a = (float)ra[xa], b = (float)ra[xb], c = (float)rb[xa], d = (float)rb[xb];
+        const float a = (float)((unsigned)ra[xa] >> p.in_shift), b = (float)((unsigned)ra[xb] >> p.in_shift), c = (float)((unsigned)rb[xa] >> p.in_shift), d = (float)((unsigned)rb[xb] >> p.in_shift);
         const float wya = (Y & 1) ? 3.0f : 1.0f, wyb = 4.0f - wya, wxa = (X & 1) ? 3.0f : 1.0f, wxb = 4.0f - wxa;
         const float va = ffma(wya, a, fmul(wyb, c)), vb = ffma(wya, b, fmul(wyb, d));      // exact integers < 2^24
         return floorf(fmul(fadd(ffma(wxa, va, fmul(wxb, vb)), 8.0f), 0.0625f));
@@ -220,41 +220,40 @@ struct ChromaParams {
     int c_in_w, c_in_h, c_W, c_H;
     const int *c_xmap, *c_xw, *c_ymap, *c_yw;
     int c_denx, c_deny;
+    int comps, shift;        // 2: one semi-planar plane (U, V interleaved);  samples carry their value in the high bits (P010: 6)
     const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done; unsigned *err_flag;
 };
+// Work is cut over "virtual planes" vp = plane * comps + component: planar chroma has two planes of one component, semi-planar
+// chroma (NV12 / P010, what NVDEC and NVENC use) one plane of two interleaved components.
 template <typename PixT>
 __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int nslices, int ct)
 {
-    struct { int chroma_n; struct { const void *in; size_t in_pitch; void *out; size_t out_pitch; } chroma[2]; int c_in_w, c_in_h, c_W, c_H;
-             const int *c_xmap, *c_xw, *c_ymap, *c_yw; int c_denx, c_deny; const unsigned *chroma_ready; unsigned chroma_seq; unsigned *chroma_done; } p;
-    p.chroma_n = cp.chroma_n;
-    for (int i = 0; i < 2; ++i) { p.chroma[i].in = cp.in[i]; p.chroma[i].in_pitch = cp.in_pitch[i]; p.chroma[i].out = cp.out[i]; p.chroma[i].out_pitch = cp.out_pitch[i]; }
-    p.c_in_w = cp.c_in_w; p.c_in_h = cp.c_in_h; p.c_W = cp.c_W; p.c_H = cp.c_H;
-    p.c_xmap = cp.c_xmap; p.c_xw = cp.c_xw; p.c_ymap = cp.c_ymap; p.c_yw = cp.c_yw; p.c_denx = cp.c_denx; p.c_deny = cp.c_deny;
-    p.chroma_ready = cp.chroma_ready; p.chroma_seq = cp.chroma_seq; p.chroma_done = cp.chroma_done;
+    const ChromaParams &p = cp;
+    const int comps = p.comps, shift = p.shift, nvp = p.chroma_n * comps;
     if (sl == 0 && p.chroma_ready) {                                 // the planes' H2D copies run on their own stream
-        if (ct == 0) spin_wait_flag(p.chroma_ready, p.chroma_seq, cp.err_flag);
+        if (ct == 0) spin_wait_flag(p.chroma_ready, p.chroma_seq, p.err_flag);
         group_sync(BAR_CONS, NCT);
     }
     if (p.c_W == 2 * p.c_in_w && p.c_H == 2 * p.c_in_h && p.c_denx == 4 && p.c_deny == 4) {
         // exact 2x: one item = 2 output rows x 8 output columns from a 3 x 6 low-res window (replicate border = clamped
         // coordinates); even outputs weigh low-res (i-1, i) by (1,3), odd outputs (i, i+1) by (3,1): (9a+3b+3c+d+8)>>4
         const int gw8 = (p.c_W + 7) / 8, per_plane8 = gw8 * p.c_in_h;
-        const long long total8 = (long long)p.chroma_n * per_plane8;
+        const long long total8 = (long long)nvp * per_plane8;
         const int c0 = (int)(total8 * blockIdx.x / gridDim.x), c1 = (int)(total8 * (blockIdx.x + 1) / gridDim.x);
         const int s0 = c0 + (int)((long long)(c1 - c0) * sl / nslices), s1 = c0 + (int)((long long)(c1 - c0) * (sl + 1) / nslices);
         for (int idx = s0 + ct; idx < s1; idx += NCT) {
-            const int pl = idx / per_plane8, rem = idx - pl * per_plane8;
+            const int vp = idx / per_plane8, rem = idx - vp * per_plane8;
+            const int pl = vp / comps, cc = vp - pl * comps;
             const int jb = rem / gw8, ib = rem - jb * gw8;
-            const char *ibase = static_cast<const char *>(p.chroma[pl].in);
-            const PixT *rows[3] = {reinterpret_cast<const PixT *>(ibase + (size_t)max(jb - 1, 0) * p.chroma[pl].in_pitch),
-                                   reinterpret_cast<const PixT *>(ibase + (size_t)jb * p.chroma[pl].in_pitch),
-                                   reinterpret_cast<const PixT *>(ibase + (size_t)min(jb + 1, p.c_in_h - 1) * p.chroma[pl].in_pitch)};
+            const char *ibase = static_cast<const char *>(p.in[pl]);
+            const PixT *rows[3] = {reinterpret_cast<const PixT *>(ibase + (size_t)max(jb - 1, 0) * p.in_pitch[pl]),
+                                   reinterpret_cast<const PixT *>(ibase + (size_t)jb * p.in_pitch[pl]),
+                                   reinterpret_cast<const PixT *>(ibase + (size_t)min(jb + 1, p.c_in_h - 1) * p.in_pitch[pl])};
             unsigned L[3][6];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int k = 0; k < 6; ++k) L[r][k] = rows[r][min(max(4 * ib - 1 + k, 0), p.c_in_w - 1)];
+                for (int k = 0; k < 6; ++k) L[r][k] = (unsigned)rows[r][min(max(4 * ib - 1 + k, 0), p.c_in_w - 1) * comps + cc] >> shift;
             unsigned o[2][8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -262,14 +261,14 @@ __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int 
                 unsigned h[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) h[r] = (e & 1) ? 3u * L[r][m + 1] + L[r][m + 2] : L[r][m] + 3u * L[r][m + 1];
-                o[0][e] = (h[0] + 3u * h[1] + 8u) >> 4;
-                o[1][e] = (3u * h[1] + h[2] + 8u) >> 4;
+                o[0][e] = ((h[0] + 3u * h[1] + 8u) >> 4) << shift;
+                o[1][e] = ((3u * h[1] + h[2] + 8u) >> 4) << shift;
             }
             const int X = 8 * ib;
 #pragma unroll
             for (int yy = 0; yy < 2; ++yy) {
-                PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.chroma[pl].out) + (size_t)(2 * jb + yy) * p.chroma[pl].out_pitch) + X;
-                const bool vec = (reinterpret_cast<uintptr_t>(orow) % (8 * sizeof(PixT))) == 0 && X + 7 < p.c_W;
+                PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out[pl]) + (size_t)(2 * jb + yy) * p.out_pitch[pl]) + X * comps + cc;
+                const bool vec = comps == 1 && (reinterpret_cast<uintptr_t>(orow) % (8 * sizeof(PixT))) == 0 && X + 7 < p.c_W;
                 if (vec && sizeof(PixT) == 1) {
                     *reinterpret_cast<uint2 *>(orow) = make_uint2(o[yy][0] | (o[yy][1] << 8) | (o[yy][2] << 16) | (o[yy][3] << 24),
                                                                  o[yy][4] | (o[yy][5] << 8) | (o[yy][6] << 16) | (o[yy][7] << 24));
@@ -279,37 +278,37 @@ __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int 
                 } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if (X + e < p.c_W) orow[e] = (PixT)o[yy][e];
+                        if (X + e < p.c_W) orow[e * comps] = (PixT)o[yy][e];
                 }
             }
         }
     } else {
-    PassParams pc{};
-    pc.in_w = p.c_in_w; pc.in_h = p.c_in_h; pc.xmap = p.c_xmap; pc.xw = p.c_xw; pc.ymap = p.c_ymap; pc.yw = p.c_yw;
-    pc.denx = p.c_denx; pc.deny = p.c_deny;
-    const int gw = (p.c_W + 3) / 4;
-    const int per_plane = gw * p.c_H;
-    const long long total = (long long)p.chroma_n * per_plane;
-    const int c0 = (int)(total * blockIdx.x / gridDim.x), c1 = (int)(total * (blockIdx.x + 1) / gridDim.x);   // this CTA's groups
-    const int s0 = c0 + (int)((long long)(c1 - c0) * sl / nslices), s1 = c0 + (int)((long long)(c1 - c0) * (sl + 1) / nslices);
-    for (int idx = s0 + ct; idx < s1; idx += NCT) {
-        const int pl = idx / per_plane, rem = idx - pl * per_plane;
-        const int Y = rem / gw, X = (rem - Y * gw) * 4;
-        pc.in = p.chroma[pl].in; pc.in_pitch = p.chroma[pl].in_pitch;
-        PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.chroma[pl].out) + (size_t)Y * p.chroma[pl].out_pitch) + X;
-        unsigned v[4];
+        PassParams pc{};
+        pc.in_w = p.c_in_w; pc.in_h = p.c_in_h; pc.xmap = p.c_xmap; pc.xw = p.c_xw; pc.ymap = p.c_ymap; pc.yw = p.c_yw;
+        pc.denx = p.c_denx; pc.deny = p.c_deny;
+        const int gw = (p.c_W + 3) / 4;
+        const int per_plane = gw * p.c_H;
+        const long long total = (long long)nvp * per_plane;
+        const int c0 = (int)(total * blockIdx.x / gridDim.x), c1 = (int)(total * (blockIdx.x + 1) / gridDim.x);   // this CTA's groups
+        const int s0 = c0 + (int)((long long)(c1 - c0) * sl / nslices), s1 = c0 + (int)((long long)(c1 - c0) * (sl + 1) / nslices);
+        for (int idx = s0 + ct; idx < s1; idx += NCT) {
+            const int vp = idx / per_plane, rem = idx - vp * per_plane;
+            const int pl = vp / comps, cc = vp - pl * comps;
+            const int Y = rem / gw, X = (rem - Y * gw) * 4;
+            PixT *orow = reinterpret_cast<PixT *>(static_cast<char *>(p.out[pl]) + (size_t)Y * p.out_pitch[pl]) + X * comps + cc;
+            unsigned v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = (X + e < p.c_W) ? (unsigned)(int)load_S<PixT>(pc, Y, X + e, true) : 0u;
-        const bool vec = ((reinterpret_cast<uintptr_t>(orow) % (4 * sizeof(PixT))) == 0) && X + 3 < p.c_W;
-        if (vec) {
-            if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-            else *reinterpret_cast<uint2 *>(orow) = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-        } else {
+            for (int e = 0; e < 4; ++e) v[e] = (X + e < p.c_W) ? bilinear_sample<PixT>(pc, p.in[pl], p.in_pitch[pl], Y, X + e, comps, cc, shift) << shift : 0u;
+            const bool vec = comps == 1 && ((reinterpret_cast<uintptr_t>(orow) % (4 * sizeof(PixT))) == 0) && X + 3 < p.c_W;
+            if (vec) {
+                if (sizeof(PixT) == 1) *reinterpret_cast<uint32_t *>(orow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                else *reinterpret_cast<uint2 *>(orow) = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (X + e < p.c_W) orow[e] = (PixT)v[e];
+                for (int e = 0; e < 4; ++e)
+                    if (X + e < p.c_W) orow[e * comps] = (PixT)v[e];
+            }
         }
-    }
     }
     if (sl == nslices - 1 && p.chroma_done) {                        // this CTA's share is written: tell the host's copy stream
         group_sync(BAR_CONS, NCT);
@@ -319,7 +318,6 @@ __device__ __noinline__ void chroma_slice_fn(const ChromaParams cp, int sl, int 
         }
     }
 }
-
 
 // ---- state a thread carries across the passes of ONE launch ------------------------------------------------------------
 struct PipeCarry {
@@ -393,8 +391,8 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
         const int xa = min(max(i, 0), p.in_w - 1), xb = min(max(i + 1, 0), p.in_w - 1);
         const PixT *ra = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)ya * p.in_pitch);
         const PixT *rb = reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yb * p.in_pitch);
-        ab = (unsigned)ra[xa] | ((unsigned)ra[xb] << 16);
-        cd = (unsigned)rb[xa] | ((unsigned)rb[xb] << 16);
+        ab = ((unsigned)ra[xa] >> p.in_shift) | (((unsigned)ra[xb] >> p.in_shift) << 16);
+        cd = ((unsigned)rb[xa] >> p.in_shift) | (((unsigned)rb[xb] >> p.in_shift) << 16);
     };
     auto store_block = [&](int s, int t, unsigned ab, unsigned cd) {
         const float a = (float)(ab & 0xffffu), b = (float)(ab >> 16), c = (float)(cd & 0xffffu), d = (float)(cd >> 16);
@@ -653,6 +651,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
         for (int i = 0; i < 2; ++i) { cp.in[i] = p.chroma[i].in; cp.in_pitch[i] = p.chroma[i].in_pitch; cp.out[i] = p.chroma[i].out; cp.out_pitch[i] = p.chroma[i].out_pitch; }
         cp.c_in_w = p.c_in_w; cp.c_in_h = p.c_in_h; cp.c_W = p.c_W; cp.c_H = p.c_H;
         cp.c_xmap = p.c_xmap; cp.c_xw = p.c_xw; cp.c_ymap = p.c_ymap; cp.c_yw = p.c_yw; cp.c_denx = p.c_denx; cp.c_deny = p.c_deny;
+        cp.comps = p.c_comps; cp.shift = p.c_shift;
         cp.chroma_ready = p.chroma_ready; cp.chroma_seq = p.chroma_seq; cp.chroma_done = p.chroma_done; cp.err_flag = p.err_flag;
         chroma_slice_fn<PixT>(cp, sl, nslices, ct);
     };
@@ -695,7 +694,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             for (int idx = ct; idx < lrh * LRW; idx += NCT) {
                 const int ly = idx / LRW, lx = idx - ly * LRW;
                 const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
-                sL[ly * LRP + lx] = (float)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx];
+                sL[ly * LRP + lx] = (float)((unsigned)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx] >> p.in_shift);
             }
             group_sync(BAR_CONS, NCT);
             for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
