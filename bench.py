@@ -539,6 +539,26 @@ def main():
     del wl, hs
 
     peak, how = measured_peaks()
+    w_h = HEAD["size"]
+
+    # ================================== opt-in numerics on the headline workload (N=1): kernel time only ====================
+    variants = {}
+    if world == 1 and not args.no_configs:
+        for vname, vnum in (("fp16_filter (RAISR_CUDA_NUMERICS=3)", 3), ("fast_hash (RAISR_CUDA_NUMERICS=4)", 4)):
+            try:
+                wv = Workload(HEAD, nbuf=12)
+                wv.eng.close()
+                with quiet_stdout():
+                    wv.eng = B.Engine(T.filter_folder(HEAD["folder"]), 2.0, 8, T.VideoRange, 1, 1, device=local, numerics=vnum)
+                wv.eng.set_res(w_h[0], w_h[1], 2 * w_h[0], 2 * w_h[1], w_h[0] // 2, w_h[1] // 2, w_h[0], w_h[1])
+                wv.time_device(wv.luma_only, 32)
+                variants[vname] = {"kernel_ms": wv.time_device(wv.luma_only, 128) / 128,
+                                   "note": "opt-in, NOT bit-identical: error bounds in DESIGN.md section 2, asserted by tests/test_gpu_fp16.py"}
+                wv.close()
+                del wv
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                variants[vname] = {"error": repr(ex)}
 
     # ================================== sub-records of the other configurations (N=1) =======================================
     sub = {}
@@ -598,7 +618,7 @@ def main():
             "e2e_pageable": {"value": e2e_pageable, "unit": "frames/s", "api": "RNLHandler_Process, pageable host planes (malloc)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "raisr_pass_pipe_kernel<uint8_t,4,1>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "raisr_frame_pipe_kernel<uint8_t,4,1,-1,0>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_Y,
                          "note": "on-chip bound stencil (shared-memory pipe + issue slots), see DESIGN.md section 4"},
@@ -606,6 +626,8 @@ def main():
         }
         if sub:
             line["configs"] = sub
+        if variants:
+            line["numerics_variants"] = variants
         if rowband is not None:
             line["rowband"] = rowband
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")

@@ -232,8 +232,9 @@ def test_randomness_blending_vs_oracle(folder, ratio, bits, passes, mode, size, 
     ("filters_2x/filters_highres", 2.0, 8, 2, 1, (150, 66)),            # fewer tiles than SMs: CTAs without a pass-1 tile
 ])
 def test_chained_passes_equal_one_launch_per_pass(folder, ratio, bits, passes, mode, size, monkeypatch):
-    """Default: both passes in one cooperative launch (pass-2 tiles wait for the pass-1 tile rows they read).  Must be bit-identical
-    to RAISR_CUDA_CHAIN=0 (a kernel boundary between the passes) -- buckets of both passes and Y -- and use a single launch."""
+    """Both passes in one cooperative launch (pass-2 tiles wait for the pass-1 tile rows they read; the default for mode 2 and 1.5x,
+    RAISR_CUDA_CHAIN=1 for every pair).  Must be bit-identical to RAISR_CUDA_CHAIN=0 (a kernel boundary between the passes) --
+    buckets of both passes and Y -- and use a single launch."""
     w, h = size
     f = T.filter_folder(folder)
     img = T.synth_frame(w, h, bits, seed=909 + w, kind="mix")
@@ -252,6 +253,7 @@ def test_chained_passes_equal_one_launch_per_pass(folder, ratio, bits, passes, m
         eng.close()
         return out, hs, n
 
+    monkeypatch.setenv("RAISR_CUDA_CHAIN", "1")                      # (the default chains only where it was measured faster)
     chained, hc, nc = run()
     monkeypatch.setenv("RAISR_CUDA_CHAIN", "0")
     split, hs, ns = run()

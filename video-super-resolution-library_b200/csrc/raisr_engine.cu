@@ -208,7 +208,8 @@ struct raisr_cuda_engine {
     bool test_drop_in_flag = false; // RAISR_CUDA_TEST_DROP_IN_FLAG=1 (tests only): drop the split-H2D flag of the first frame
     bool fast_hash = false;         // RAISR_NUMERICS_FAST_HASH: separable structure tensor (opt-in, buckets not bit-identical)
     bool filter_fp16 = false;       // RAISR_NUMERICS_FP16_FILTER: half-precision filter stage (opt-in, Y not bit-identical); the hash keeps cfg.numerics
-    bool chain_passes = true;       // two-pass configurations in one persistent launch; RAISR_CUDA_CHAIN=0: one launch per pass
+    int chain_passes = -1;          // two-pass configurations in one persistent launch: -1 = where measured faster (see launch_chained),
+                                    // RAISR_CUDA_CHAIN=1: always, RAISR_CUDA_CHAIN=0: never (one launch per pass)
     bool coop_launch = false;       // device supports cooperative launches (needed by the chained launch)
     unsigned *d_rows_done = nullptr; int rows_done_cap = 0;   // chained launch: finished tiles per tile row of the first pass
     void *d_filters16[2] = {nullptr, nullptr};                 // fp16 copies of the filter tables (filter_fp16 only)
@@ -368,6 +369,11 @@ int launch_chained(raisr_cuda_engine *e, const PassParams &p1, const PassParams 
     if (!e->use_pipe || !e->chain_passes || !e->coop_launch || !e->d_rows_done) return -1;
     PassPlan a = plan_pass(e, p1), b = plan_pass(e, p2);
     if ((int)a.grid.y > e->rows_done_cap) return -1;
+    // Default policy = what was measured (same box, luma passes of a frame, chained vs one launch per pass): mode 2 at 2x
+    // 0.732 vs 0.761 ms (1080p->4K) and 2.636 vs 2.670 ms (4K->8K), 1.5x 0.285 vs 0.296 ms -- chained wins; mode 1 at 2x (exact-2x
+    // upscale in pass 1, plain pass 2) 1.173 vs 1.151 ms -- the boundary-free launch loses 2 % to the register allocation of its
+    // second inlined pass, so that pair runs as two launches unless RAISR_CUDA_CHAIN=1 asks for the chained form.
+    if (e->chain_passes < 0 && p1.ptypes == 4 && a.ups == 1 && b.ups == 0) return -1;
     FrameLaunch fl;
     fl.a = a.q; fl.b = b.q; fl.two = true; fl.ups_a = a.ups; fl.ups_b = b.ups; fl.stream = s;
     fl.a.rows_done = e->d_rows_done;
@@ -600,7 +606,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     // 16-bit samples (not reachable from the FFmpeg filter: bits = 8..10, vf_raisr.c:83) run on the phase-sequential kernel: the
     // pipelined kernel reads its Gaussian weights from immutable constant tables that exist for 8 and 10 bit (raisr_gw_tables.h)
     if (cfg->bit_depth == 16) e->use_pipe = false;
-    if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0;
+    if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0 ? 1 : 0;
     if (const char *c = std::getenv("RAISR_CUDA_TEST_DROP_IN_FLAG")) e->test_drop_in_flag = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));

@@ -755,17 +755,20 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             // same additions as tree8() end up in lanes q & 3 == u (both halves q < 4 and q >= 4 hold the final sum).
             const unsigned hbase = smem_u32(sHash) + (unsigned)(g * JS);
             const unsigned lastrow = (unsigned)p.nbuckets - 1u;
-            auto fast_block = [&](auto uu, const int h, const int jc0) {   // h, jc0 (block column 0) are warp-uniform
+            // One warp item = one tile row of this pixel type (NBLK blocks of 4 pixel groups), software-pipelined over its blocks: the
+            // loads and FMAs of block b+1 are issued before the lane tree of block b (two register sets alternate), so the shuffle
+            // latency of the tree hides under the next block's shared-memory loads.  The filter warps are bound by exactly that
+            // stream of loads, not by issue slots or total shared-memory traffic: this alone took the 4K frame from 0.593 to 0.567 ms.
+            // (Rows outside [6, H-6) are skipped; columns from c_end on carry bucket 255 and drop their result.)
+            auto blk_mac = [&](auto uu, const int h, const int jc0, f32x2 (&acc)[4], unsigned (&acch)[4], unsigned (&hv)[4]) {
                 constexpr int UU = decltype(uu)::value;
                 const unsigned ub = 4u * (unsigned)(h * SP + jc0);
                 const unsigned hva = hbase + (unsigned)(h * HP + jc0);
-                unsigned hv[4], fa[4];
+                unsigned fa[4];
                 hv[0] = lds_u8<0>(hva); hv[1] = lds_u8<4 * JS>(hva);
                 hv[2] = (UU > 2) ? lds_u8<8 * JS>(hva) : 255u; hv[3] = (UU > 3) ? lds_u8<12 * JS>(hva) : 255u;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) fa[u] = fbase + (min(hv[u], lastrow) << ROWSH);   // 255 (not hashed): any row of the slice, result dropped
-                f32x2 acc[4];                                                 // fp32: (chain 2q, chain 2q+1);  F16: .x of the pair holds the half2
-                unsigned acch[4];
+                for (int u = 0; u < 4; ++u) fa[u] = fbase + (min(hv[u], lastrow) << ROWSH);
                 auto step = [&](auto nn) {
                     constexpr int n = decltype(nn)::value;
                     const unsigned q0 = poff[2 * n][0] + ub, q1 = poff[2 * n][1] + ub, q2 = poff[2 * n + 1][0] + ub, q3 = poff[2 * n + 1][1] + ub;
@@ -773,7 +776,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                         constexpr int u = decltype(uc)::value;
                         if (u < UU) {
                             if (F16) {
-                                unsigned f01, f23;                            // half2 coefficients of chunks 2n and 2n+1
+                                unsigned f01, f23;
                                 lds_b32x2<n * 64>(fa[u], f01, f23);
                                 const unsigned p01 = f2h2(lds_f32<16 * JS * u>(q0), lds_f32<16 * JS * u>(q1));
                                 const unsigned p23 = f2h2(lds_f32<16 * JS * u>(q2), lds_f32<16 * JS * u>(q3));
@@ -794,7 +797,9 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 };
                 step(std::integral_constant<int, 0>{}); step(std::integral_constant<int, 1>{});
                 step(std::integral_constant<int, 2>{}); step(std::integral_constant<int, 3>{});
-                // t8: lanes q < 4 keep chain 2q and take chain 2q of lane q+4; lanes q >= 4 keep chain 2q+1 and take it from lane q-4
+            };
+            auto blk_fin = [&](auto uu, const int h, const int jc0, const f32x2 (&acc)[4], const unsigned (&acch)[4], const unsigned (&hv)[4]) {
+                constexpr int UU = decltype(uu)::value;
                 const bool hi4 = q >= 4, b1 = (q & 2) != 0, b0 = (q & 1) != 0;
                 float v[4];
 #pragma unroll
@@ -805,37 +810,49 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                         v[u] = fadd(hi4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi4 ? a0 : a1, 4, 8));
                     } else v[u] = 0.0f;
                 }
-                // t4: lanes with q & 2 keep pixels 2,3 and send 0,1; the others keep 0,1 and send 2,3
                 const float w0 = fadd(b1 ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2, 8));
                 const float w1 = fadd(b1 ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2, 8));
-                // t2: lanes with q & 1 keep the odd pixel
                 const float x = fadd(b0 ? w1 : w0, __shfl_xor_sync(0xffffffffu, b0 ? w0 : w1, 1, 8));
-                const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));      // t2[0] + t2[1]: pixel u = q & 3
+                const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));
                 const unsigned hu = b1 ? (b0 ? hv[3] : hv[2]) : (b0 ? hv[1] : hv[0]);
-                if (q < 4 && hu != 255u && cur > flo && cur < fhi)              // strict range test, Raisr.cpp:1192-1196
+                if (q < 4 && hu != 255u && cur > flo && cur < fhi)
                     sts_f32(hroff + 4u * (unsigned)(h * HP + jc0), cur);
             };
-            // whole rounds of (row, block) items, one item per warp; the items of the last, partial round are split into
-            // single pixel groups over all warps so that no warp waits a whole item at the barrier.  Items without a hashed
-            // pixel (rows outside [6, H-6), columns from c_end on) are skipped: HR stays S there.
-            const int nitems = nrows * NBLK, nfull = (nitems / NCW) * NCW;
-            auto live = [&](int h, int jc0) {
-                const int r = y0 - 1 + h;
-                return r >= 6 && r < H - 6 && x0 - 1 + jc0 < p.c_end;
+            // (Measured: carrying the pipeline on from one row of the warp to the next -- last block of a row finished under the first
+            // block of the following row -- keeps both register sets live across the loop and costs more than it hides: 0.599 vs 0.567 ms.)
+            // Items are row SEGMENTS of SEG = 4 blocks (4 pixel types: the whole row; one pixel type: half a row, which balances the
+            // 12 warps better); the last block of a row is shorter (ULAST groups).
+            constexpr int SEG = 4, NSEG = (NBLK + SEG - 1) / SEG;
+            static_assert(NBLK == 4 || NBLK == 8, "row segments of 4 blocks");
+            auto run_seg = [&](auto lastc, const int h, const int jbase) {
+                constexpr bool LASTSEG = decltype(lastc)::value;
+                f32x2 A[2][4];
+                unsigned AH[2][4], HV[2][4];
+                auto mac_b = [&](auto bc) {
+                    constexpr int bb = decltype(bc)::value;
+                    const int jc0 = jbase + bb * 4 * U * JS;
+                    if constexpr (LASTSEG && bb == SEG - 1) blk_mac(std::integral_constant<int, ULAST>{}, h, jc0, A[bb & 1], AH[bb & 1], HV[bb & 1]);
+                    else blk_mac(std::integral_constant<int, U>{}, h, jc0, A[bb & 1], AH[bb & 1], HV[bb & 1]);
+                };
+                auto fin_b = [&](auto bc) {
+                    constexpr int bb = decltype(bc)::value;
+                    const int jc0 = jbase + bb * 4 * U * JS;
+                    if constexpr (LASTSEG && bb == SEG - 1) blk_fin(std::integral_constant<int, ULAST>{}, h, jc0, A[bb & 1], AH[bb & 1], HV[bb & 1]);
+                    else blk_fin(std::integral_constant<int, U>{}, h, jc0, A[bb & 1], AH[bb & 1], HV[bb & 1]);
+                };
+                mac_b(std::integral_constant<int, 0>{});
+                mac_b(std::integral_constant<int, 1>{}); fin_b(std::integral_constant<int, 0>{});
+                mac_b(std::integral_constant<int, 2>{}); fin_b(std::integral_constant<int, 1>{});
+                mac_b(std::integral_constant<int, 3>{}); fin_b(std::integral_constant<int, 2>{});
+                fin_b(std::integral_constant<int, 3>{});
             };
-            for (int it = cwarp; it < nfull; it += NCW) {
-                const int ri = it / NBLK, bi = it - ri * NBLK;
-                const int h = hfirst + ri * JS, jc0 = jfirst + bi * 4 * U * JS;
-                if (!live(h, jc0)) continue;
-                if (bi < NBLK - 1) fast_block(std::integral_constant<int, U>{}, h, jc0);
-                else fast_block(std::integral_constant<int, ULAST>{}, h, jc0);
-            }
-            for (int rq = cwarp; rq < (nitems - nfull) * U; rq += NCW) {
-                const int it = nfull + rq / U, u = rq - (rq / U) * U;
-                const int ri = it / NBLK, bi = it - ri * NBLK;
-                const int h = hfirst + ri * JS, jc0 = jfirst + (bi * 4 * U + 4 * u) * JS;
-                if ((bi == NBLK - 1 && u >= ULAST) || !live(h, jc0)) continue;
-                fast_block(std::integral_constant<int, 1>{}, h, jc0);
+            for (int it = cwarp; it < nrows * NSEG; it += NCW) {
+                const int ri = it / NSEG, sg = it - ri * NSEG;
+                const int h = hfirst + ri * JS, r = y0 - 1 + h;
+                const int jbase = jfirst + sg * SEG * 4 * U * JS;
+                if (r < 6 || r >= H - 6 || x0 - 1 + jbase >= p.c_end) continue;
+                if (sg == NSEG - 1) run_seg(std::true_type{}, h, jbase);
+                else if constexpr (NSEG > 1) run_seg(std::false_type{}, h, jbase);
             }
             // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
             // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
