@@ -95,6 +95,25 @@ template <int IMM> __device__ __forceinline__ void lds_b32x2(unsigned a, unsigne
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(lo), "=r"(hi) : "r"(a), "n"(IMM));
 }
 
+// compile-time loop: f(std::integral_constant<int, 0>{}) ... f(std::integral_constant<int, N - 1>{})
+template <int I, int N, typename F> __device__ __forceinline__ void static_for_impl(F &f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for_impl<I + 1, N>(f);
+    }
+}
+template <int N, typename F> __device__ __forceinline__ void static_for(F &&f) { static_for_impl<0, N>(f); }
+
+// Sliding-window form of stage D (exact fp32 filter): see pipe_filter_pass.  Shuffle sources of its folded lane tree, packed per
+// lane-in-group q -- per 4-step unit (bits 0..15: steps 0..3, bits 16..31: steps 4..7): source lanes of level 2 (3 + 3 bits) and
+// level 3 (3 bits), then one bit per step "this lane keeps the odd chain at level 1".  Generated AND verified (symbolically, against
+// the reference's chain and tree order) by tools/slide_model.py.
+#ifndef RAISR_STAGE_D_SLIDE
+#define RAISR_STAGE_D_SLIDE 1
+#endif
+static __constant__ unsigned c_slide_tbl[8] = {0x0a521452u, 0x1a3b043bu, 0x12e40ce4u, 0x168d088du, 0x15760b76u, 0x051f1b1fu, 0x0dc013c0u, 0x09a917a9u};
+
 // Half-precision pairs of the opt-in fp16 filter stage: IEEE binary16, round to nearest even (HMUL2 / HFMA2: one rounding per
 // operation, like the vmulph / vfmadd...ph of the reference's AVX512-FP16 dot product, Raisr_AVX512FP16.cpp:227-242).
 __device__ __forceinline__ unsigned f2h2(float lo, float hi) { unsigned r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
@@ -629,14 +648,34 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
     const float flo = (float)p.lo, fhi = (float)p.hi;
     const int slice_bytes = p.nbuckets * ROWB;
     // per-lane constant parts of the fast block's shared addresses (bytes): pixel group g, lane q of the group
+    constexpr bool SLIDE = (RAISR_STAGE_D_SLIDE != 0) && !F16;         // sliding-window form of stage D (below)
     unsigned poff[8][2];                                              // patch tap (m, e) of the group's pixel in block column 0
+    if constexpr (!SLIDE) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
+        for (int m = 0; m < 8; ++m)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            poff[m][e] = smem_u32(sS) + 4u * (unsigned)(off[m][e] + SP + 1 + g * JS);
-            asm volatile("" : "+r"(poff[m][e]));                      // keep the 16 addresses in registers (no rematerialisation per block)
+            for (int e = 0; e < 2; ++e) {
+                poff[m][e] = smem_u32(sS) + 4u * (unsigned)(off[m][e] + SP + 1 + g * JS);
+                asm volatile("" : "+r"(poff[m][e]));                  // keep the 16 addresses in registers (no rematerialisation per block)
+            }
+    }
+    // sliding form: the lane's own positions of the column strip of pixel group g, linearised as k0 = 11 R + c (R = strip row, c =
+    // patch column): ring slot s holds the pair k0 = 16 s + 2q, 16 s + 2q + 1 (and, 16 strip rows further down, the pair s + 11)
+    unsigned spk[11];                                                 // packed: low half = byte offset of the pair's first tap in the S tile, high half = second tap
+    unsigned stbl = 0u, hrlane = 0u, hlane = 0u;
+    if constexpr (SLIDE) {
+#pragma unroll
+        for (int s = 0; s < 11; ++s) {
+            const int k = 16 * s + 2 * q;
+            const unsigned ox = 4u * (unsigned)((k / 11) * SP + (k % 11) + SP + 1 + g * JS);
+            const unsigned oy = 4u * (unsigned)(((k + 1) / 11) * SP + ((k + 1) % 11) + SP + 1 + g * JS);
+            spk[s] = ox | (oy << 16);
+            asm volatile("" : "+r"(spk[s]));                          // keep the 11 words in registers (no rematerialisation per item)
         }
+        stbl = c_slide_tbl[q];
+        hrlane = smem_u32(sHR) + 4u * (unsigned)(g * JS + 2 * (q & 3) * HP);   // HR cell of the pixel whose sum ends up in this lane (step q & 3 of a unit)
+        hlane = (unsigned)(g * JS + 2 * (q & 3) * HP);                        // ... and its bucket
+    }
     const unsigned fbase = smem_u32(sF) + (unsigned)(ROWB / 32) * (unsigned)q;   // this lane's 16 (fp16: 8) bytes of every filter step
     const unsigned hroff = smem_u32(sHR) + 4u * (unsigned)((g + 4 * (q & 3)) * JS);   // HR column of the pixel whose sum ends up in this lane
     // ---- chroma planes: plain cheap upscale (Raisr.cpp:1373-1388), 4 pixels per thread.  This CTA's share of the planes is
@@ -846,6 +885,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 mac_b(std::integral_constant<int, 3>{}); fin_b(std::integral_constant<int, 2>{});
                 fin_b(std::integral_constant<int, 3>{});
             };
+            if constexpr (!SLIDE) {
             for (int it = cwarp; it < nrows * NSEG; it += NCW) {
                 const int ri = it / NSEG, sg = it - ri * NSEG;
                 const int h = hfirst + ri * JS, r = y0 - 1 + h;
@@ -853,6 +893,106 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 if (r < 6 || r >= H - 6 || x0 - 1 + jbase >= p.c_end) continue;
                 if (sg == NSEG - 1) run_seg(std::true_type{}, h, jbase);
                 else if constexpr (NSEG > 1) run_seg(std::false_type{}, h, jbase);
+            }
+            } else {
+            // ---- sliding-window form (the default of the exact fp32 filter) ----
+            // A pixel group (8 lanes) walks DOWN a column of same-type pixels, two tile rows per step, and keeps its patch values in
+            // registers.  Linearise the column strip as k0 = 11 R + c: the taps of the pixel of step N are k0 in [22 N, 22 N + 121), tap
+            // k = k0 - 22 N.  Lane q owns the positions k0 = 2q, 2q + 1 (mod 16) for the whole walk; at step N these are exactly the
+            // taps of the chain pair p = (q - 3N) & 7, in chain order: the ownership of the reference's 16 chains (Raisr_AVX512.cpp:
+            // 134-149: chain j = taps 16 m + j, m = 0..7, then the 16-lane tree) ROTATES through the lanes instead of the values moving.
+            // Per step a lane loads the 1.4 new tap pairs that enter the strip window (ring of 11 pairs = the period of 8 steps = 16
+            // strip rows) instead of all 16 taps: 2.75 instead of 16 patch loads per pixel and lane.  The chain of lanes q < 3N mod 8
+            // starts one pair later than that of the others; both alignments are accumulated (two independent FFMA2 chains against
+            // the same coefficient registers) and the lane selects its own.  The lane tree is the same folded tree as before, with
+            // shuffle sources from c_slide_tbl (the chain pairs sit in rotated lanes).  Schedule and tree are verified symbolically
+            // by tools/slide_model.py; results are bit-identical to the block form above (same products, same order).
+            // Positions past the strip of the last pixel (pairs a lane loads but does not own taps in) meet coefficient zero.
+            constexpr int NCB = (NCOLS + 3) / 4;                          // column blocks: 4 pixel groups side by side
+            constexpr int NWALK = (PT == 4) ? 1 : 2;                      // one pixel type: rows of both parities, two walks per column
+            const int hs0 = (PT == 4) ? hfirst : 0;
+            const int nseg = ((hh - hs0 + 1) / 2 + 7) / 8;                // walks are cut into items of 8 steps (two units of 4)
+            const unsigned lastrow_s = (unsigned)p.nbuckets - 1u;
+            const unsigned fbm = fbase - 128u;
+            auto slide_item = [&](auto twoc, const int h0, const int jc0) {
+                constexpr bool TWO = decltype(twoc)::value;
+                constexpr int NSTEP = TWO ? 8 : 4;
+                unsigned ubv = smem_u32(sS) + 4u * (unsigned)(h0 * SP + jc0);       // strip origin of this item (uniform, but wanted in a vector register:
+                asm volatile("" : "+r"(ubv));                                      //  one add per patch load instead of a uniform-to-vector move plus a multiply-add)
+                const unsigned hva = smem_u32(sHash) + (unsigned)(g * JS + h0 * HP + jc0);
+                const unsigned hul = smem_u32(sHash) + hlane + (unsigned)(h0 * HP + jc0);
+                const unsigned hra = hrlane + 4u * (unsigned)(h0 * HP + jc0);
+                float Wx[11], Wy[11];
+                f32x2 C[16];                                                      // coefficient units: step n uses C[8 (n & 1) + 0..7], the other half is being loaded
+                float v[4];
+                auto ldw = [&](auto sc, auto immc) {
+                    constexpr int sl = decltype(sc)::value, imm = decltype(immc)::value;
+                    Wx[sl] = lds_f32<imm>((spk[sl] & 0xffffu) + ubv);
+                    Wy[sl] = lds_f32<imm>((spk[sl] >> 16) + ubv);
+                };
+                auto ldc = [&](auto nc, const unsigned fa) {                        // the 4 coefficient units of step n: chain pair (q - t_n) & 7 of row fa
+                    constexpr int n = decltype(nc)::value, tn = (3 * n) % 8, cb0 = 8 * (n & 1);
+                    lds_f32x2x2<128 + 0 - 16 * tn>(fa, C[cb0 + 0], C[cb0 + 1]);
+                    lds_f32x2x2<128 + 128 - 16 * tn>(fa, C[cb0 + 2], C[cb0 + 3]);
+                    lds_f32x2x2<128 + 256 - 16 * tn>(fa, C[cb0 + 4], C[cb0 + 5]);
+                    lds_f32x2x2<128 + 384 - 16 * tn>(fa, C[cb0 + 6], C[cb0 + 7]);
+                };
+                unsigned hvc = lds_u8<0>(hva), hvn = lds_u8<2 * HP>(hva);           // buckets of steps 0 and 1
+                static_for<8>([&](auto sc) { ldw(sc, std::integral_constant<int, 0>{}); });
+                ldc(std::integral_constant<int, 0>{}, fbm + (min(hvc, lastrow_s) << 9));
+                static_for<NSTEP>([&](auto nc) {
+                    constexpr int n = decltype(nc)::value;
+                    constexpr int B = 11 * n / 8, t = (3 * n) % 8, u = n & 3, cb0 = 8 * (n & 1);
+                    constexpr bool more = n + 1 < NSTEP;
+                    constexpr int tn = (3 * (n + 1)) % 8;
+                    unsigned hu = 255u;
+                    if constexpr (more) {
+                        // everything step n + 1 needs is requested before the arithmetic of step n: the pairs entering its window (their ring
+                        // slots are dead at step n), its coefficient units (other half of C), and the bucket of step n + 2
+                        constexpr int Lc = (n == 0) ? 7 : B + 8, Ln = 11 * (n + 1) / 8 + 8;
+                        static_for<Ln - Lc>([&](auto ic) {
+                            constexpr int i = Lc + 1 + decltype(ic)::value;
+                            ldw(std::integral_constant<int, i % 11>{}, std::integral_constant<int, (i >= 11) ? 16 * SP * 4 : 0>{});
+                        });
+                        ldc(std::integral_constant<int, n + 1>{}, fbm + (min(hvn, lastrow_s) << 9) + ((q < tn) ? 128u : 0u));
+                        if constexpr (n + 2 < NSTEP) hvn = lds_u8<2 * HP * (n + 2)>(hva);
+                    }
+                    if constexpr (u == 3) hu = lds_u8<2 * HP * (n - 3)>(hul);       // bucket of the pixel this lane ends up with
+                    f32x2 aU = 0ull, aF = 0ull;
+                    static_for<8>([&](auto mc) {
+                        constexpr int m = decltype(mc)::value;
+                        const f32x2 wu = pack2(Wx[(B + m) % 11], Wy[(B + m) % 11]);
+                        aU = (m == 0) ? mul2(wu, C[cb0 + m]) : fma2(wu, C[cb0 + m], aU);
+                        if constexpr (t != 0) {
+                            const f32x2 wf = pack2(Wx[(B + 1 + m) % 11], Wy[(B + 1 + m) % 11]);
+                            aF = (m == 0) ? mul2(wf, C[cb0 + m]) : fma2(wf, C[cb0 + m], aF);
+                        }
+                    });
+                    float a0, a1;
+                    if constexpr (t != 0) unpack2((q < t) ? aF : aU, a0, a1); else unpack2(aU, a0, a1);
+                    const bool hi = ((stbl >> (16 * (n >> 2) + 9 + u)) & 1u) != 0u;
+                    v[u] = fadd(hi ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 4, 8));
+                    if constexpr (u == 3) {
+                        constexpr int SH0 = 16 * (n >> 2), n0 = n - 3;
+                        const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+                        const float w0 = fadd(b1 ? v[2] : v[0], __shfl_sync(0xffffffffu, b1 ? v[0] : v[2], (int)(stbl >> SH0), 8));
+                        const float w1 = fadd(b1 ? v[3] : v[1], __shfl_sync(0xffffffffu, b1 ? v[1] : v[3], (int)(stbl >> (SH0 + 3)), 8));
+                        const float x = fadd(b0 ? w1 : w0, __shfl_sync(0xffffffffu, b0 ? w0 : w1, (int)(stbl >> (SH0 + 6)), 8));
+                        const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));
+                        if (q < 4 && hu != 255u && cur > flo && cur < fhi) sts_f32(hra + 4u * (unsigned)(2 * n0 * HP), cur);
+                    }
+                });
+            };
+            for (int it = cwarp; it < NCB * NWALK * nseg; it += NCW) {
+                const int cw = it / nseg, sg = it - cw * nseg;
+                const int wk = (NWALK == 2) ? (cw & 1) : 0, cb = (NWALK == 2) ? (cw >> 1) : cw;
+                const int hsw = hs0 + wk;
+                const int left = (hh - hsw + 1) / 2 - 8 * sg;             // steps left in this walk
+                const int h0 = hsw + 16 * sg, jc0 = jfirst + 4 * cb * JS;
+                if (left <= 0 || x0 - 1 + jc0 >= p.c_end) continue;
+                if (left > 4) slide_item(std::true_type{}, h0, jc0);
+                else slide_item(std::false_type{}, h0, jc0);
+            }
             }
             // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
             // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
