@@ -218,6 +218,10 @@ __device__ __forceinline__ void spin_wait_flag_geq(const unsigned *flag, unsigne
 // of a barrier to meet at ONE instruction and reports "divergent threads".  -DRAISR_SYNCCHECK_BUILD routes both roles through a
 // single out-of-line barrier instruction (synccheck: 0 errors, profiles/r2_sanitizer.txt); the call costs 2.5 % (0.6054 vs
 // 0.5904 ms per 4K frame), so the shipped build keeps the barrier inline.
+// (Round 2, measured and removed: splitting this hand-off so that a bucket warp no longer waits for the OTHER bucket warps -- chain ->
+// bucket over one mbarrier per chain buffer, bucket -> chain over mbarriers (0.551 ms) or over named barriers the bucket warps only
+// arrive on (0.586 ms), against 0.531 ms for the single 512-thread barrier: a waiting warp that polls takes issue slots from the warps
+// it waits for, and this kernel is bound by issue slots.  bar.sync blocks for free.)
 #ifdef RAISR_SYNCCHECK_BUILD
 static __device__ __noinline__ void producer_chunk_barrier() { group_sync_c<BAR_PROD, NPT>(); }
 #else
@@ -927,7 +931,9 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 float v[4];
                 auto ldw = [&](auto sc, auto immc) {
                     constexpr int sl = decltype(sc)::value, imm = decltype(immc)::value;
-                    Wx[sl] = lds_f32<imm>((spk[sl] & 0xffffu) + ubv);
+                    unsigned lo;                                                    // (volatile: extracted per load, not hoisted into 11 more registers)
+                    asm volatile("and.b32 %0, %1, 0xffff;" : "=r"(lo) : "r"(spk[sl]));
+                    Wx[sl] = lds_f32<imm>(lo + ubv);
                     Wy[sl] = lds_f32<imm>((spk[sl] >> 16) + ubv);
                 };
                 auto ldc = [&](auto nc, const unsigned fa) {                        // the 4 coefficient units of step n: chain pair (q - t_n) & 7 of row fa
@@ -983,8 +989,10 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                     }
                 });
             };
-            for (int it = cwarp; it < NCB * NWALK * nseg; it += NCW) {
-                const int cw = it / nseg, sg = it - cw * nseg;
+            // items in segment-major order: the divisor of the index split is a compile-time constant
+            constexpr int NCI = NCB * NWALK;
+            for (int it = cwarp; it < NCI * nseg; it += NCW) {
+                const int sg = it / NCI, cw = it - sg * NCI;
                 const int wk = (NWALK == 2) ? (cw & 1) : 0, cb = (NWALK == 2) ? (cw >> 1) : cw;
                 const int hsw = hs0 + wk;
                 const int left = (hh - hsw + 1) / 2 - 8 * sg;             // steps left in this walk
