@@ -44,9 +44,11 @@ out += L[k - 10:k + 34]
 w = find(r"SYNCS\.PHASECHK", k)
 out += ["     ..."] + L[w - 1:w + 2] + [""]
 d = find(r"LDS\.128", w)
-out.append("---- stage D, software-pipelined row segment: blocks of 4 pixel groups x 4 pixels; lane q owns reference chains 2q, 2q+1 ----------")
-out.append("     per block and step: 4 x (LDS.128 = 16 B of the pixel's filter row + 4 LDS patch taps) and 8 FFMA2; the loads of block b+1 are issued before")
-out.append("     the folded 16->1 lane tree of block b (FSEL / SHFL.BFLY / FADD) and the strict range test + STS of its results")
-out += L[d - 24:d + 330] + ["     ..."]
+out.append("---- stage D, sliding-window item: a pixel group (8 lanes) walks down a column of same-type pixels, 8 steps per item -----------------")
+out.append("     per step: 4 x LDS.128 (the pixel's coefficient units, chain pair (q - 3N) & 7 of its row), the 1-2 tap pairs that enter the")
+out.append("     strip window (LDS via LEA.HI / LOP3 of the packed per-lane offsets), 2 x 8 FMUL2/FFMA2 (the chain in both alignments, SEL picks")
+out.append("     the lane's own), level 1 of the lane tree (FSEL / SHFL.BFLY / FADD); every 4 steps the folded levels 2-4 with rotated shuffle")
+out.append("     sources (SHFL.IDX, sources from c_slide_tbl), the strict range test and the STS of the 4 results")
+out += L[d - 40:d + 300] + ["     ..."]
 open(os.path.join(ROOT, "profiles", "r2_sass_hot_loops.txt"), "w").write("\n".join(out) + "\n")
 print("wrote profiles/r2_sass_hot_loops.txt (%d lines)" % len(out))
