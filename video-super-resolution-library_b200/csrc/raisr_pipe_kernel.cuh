@@ -473,12 +473,16 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
             f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
-            float vprev = sRing[((s0) & (RING - 1)) * SP + q + 1];
-            const float *row = sRing + ((s0 + 1) & (RING - 1)) * SP + q;
+            // window row j = ring row (s0 + j) & (RING-1): one of two bases (before / after the ring wraps) plus a compile-time offset
+            const int r0 = s0 & (RING - 1), jw = RING - r0;
+            const float *pA = sRing + r0 * SP + q, *pB = pA - RING * SP;
+            auto wrow = [&](int j) { return (j < jw ? pA : pB) + j * SP; };
+            float vprev = wrow(0)[1];
+            const float *row = wrow(1);
             float vcur = row[1];
 #pragma unroll
             for (int i = 0; i < 11; ++i) {
-                const float *nrow = sRing + ((s0 + 2 + i) & (RING - 1)) * SP + q;
+                const float *nrow = wrow(2 + i);
                 const float vnext = nrow[1];
                 const float gxv = fsub(vnext, vprev);                // GetGx (Raisr_AVX512.cpp:54-57)
                 const float gyv = fsub(row[2], row[0]);              // GetGy (Raisr_AVX512.cpp:59-62)
