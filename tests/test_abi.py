@@ -153,3 +153,22 @@ def test_process_null_planes():
     P = C.byref(v)
     assert L.RNLHandler_Process(P, P, P, P, P, P, T.CountOfBitsChanged) == T.RNLErrorBadParameter
     assert L.RNLHandler_Process(None, None, None, None, None, None, T.CountOfBitsChanged) == T.RNLErrorBadParameter
+
+
+def test_sliding_window_schedule_and_tree_table():
+    """Stage D of the pipelined kernel (csrc/raisr_pipe_kernel.cuh) walks down pixel columns with rotating chain ownership.  Its
+    schedule and folded lane tree are verified symbolically against the reference's chain / tree order (DotProdPatch_AVX512_32f,
+    Raisr_AVX512.cpp:134-149, sumitup_ps_512 :37-44) by tools/slide_model.py; the shuffle-source table in the kernel header must be the
+    one that model produces."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("slide_model", os.path.join(root, "tools", "slide_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.check_macs(48)
+    words = m.tree_tables()
+    m.check_tree(words)
+    src = open(os.path.join(root, "video-super-resolution-library_b200", "csrc", "raisr_pipe_kernel.cuh")).read()
+    tbl = re.search(r"c_slide_tbl\[8\] = \{([^}]*)\}", src).group(1)
+    assert [int(x.strip().rstrip("u"), 16) for x in tbl.split(",")] == words
