@@ -25,8 +25,8 @@ out = ["SASS of the shipped hot instantiation raisr_frame_pipe_kernel<uint8_t, 4
        "(nvcc 12.9, -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo); regenerate with profiles/make_sass_excerpt.py",
        "%d instructions.  Static opcode census (whole kernel):" % len(L),
        "  " + ", ".join("%s:%d" % kv for kv in ops.most_common(26)),
-       "  sm_100-specific: FFMA2 %d + FMUL2 %d (packed fp32 pairs: two IEEE operations per issue slot), UBLKCP %d (cp.async.bulk = TMA bulk copies of the filter slices),"
-       % (ops["FFMA2"], ops["FMUL2"], ops["UBLKCP"]),
+       "  sm_100-specific: FFMA2 %d + FMUL2 %d (packed fp32 pairs: two IEEE operations per issue slot), UBLKCP %d (cp.async.bulk = TMA bulk copies of the filter slices), UTMALDG %d (tensor-map TMA load of the input window),"
+       % (ops["FFMA2"], ops["FMUL2"], ops["UBLKCP"], ops["UTMALDG"]),
        "  SYNCS %d (mbarrier), USETMAXREG %d (setmaxnreg), BAR %d (named barriers, immediate id and thread count), uniform datapath R2UR/LDCU/U* %d"
        % (ops["SYNCS"], ops["USETMAXREG"], ops["BAR"], sum(v for k, v in ops.items() if k[0] == "U" or k in ("R2UR", "LDCU"))), ""]
 out.append("---- role split: the three warp roles re-balance the register file (setmaxnreg 48 / 56 / 96) --------------------------------")
@@ -38,6 +38,10 @@ out += L[i - 6:i + 60] + ["     ...", ""]
 j = find(r"BAR\.ARV", i)
 out.append("---- bucket warps -> filter warps: bucket tile complete = bar.arrive on a named barrier (the filter side waits in bar.sync) ------")
 out += L[j - 2:j + 2] + [""]
+t = find(r"UTMALDG")
+if t >= 0:
+    out.append("---- stage A: low-res window of an interior tile by ONE tensor-map TMA load (cp.async.bulk.tensor.2d -> UTMALDG.2D) ---------------")
+    out += L[t - 16:t + 8] + [""]
 k = find(r"UBLKCP")
 out.append("---- stage D: filter slice of one pixel type by TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx), 4 pieces, then the wait --")
 out += L[k - 10:k + 34]

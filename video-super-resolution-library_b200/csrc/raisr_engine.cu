@@ -7,6 +7,7 @@
 // (the reference's pass control, Library/Raisr.cpp:896-975), plus one resize launch per chroma plane
 // (Raisr.cpp:1373-1388).  The pass-1 -> pass-2 dependency is stream order; the intermediate plane is
 // quantised to u8/u16 exactly like gIntermediateY (Raisr.cpp:919-927, 1716-1723).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -233,6 +234,16 @@ struct raisr_cuda_engine {
     cudaStream_t stream_d2h = nullptr;
     typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
     WaitValue32Fn wait_value32 = nullptr, write_value32 = nullptr;
+    // cuTensorMapEncodeTiled (driver entry point, like the stream memory operations): tensor maps of the passes' input planes for the
+    // TMA load of stage A; the last few encodings are cached by (pointer, pitch, geometry)
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+    EncodeTiledFn encode_tiled = nullptr;
+    bool use_tma = true;            // RAISR_CUDA_TMA=0: clamped scalar loads everywhere
+    struct TmapEntry { const void *ptr = nullptr; size_t pitch = 0; int w = 0, h = 0; alignas(64) CUtensorMap map; };
+    TmapEntry tmaps[4];
+    int tmap_next = 0;
     unsigned *d_in_ready = nullptr;      // sequence number of the last frame whose lower input rows (split H2D) have arrived
     unsigned frame_seq = 0;
     // pageable caller planes: page-locked staging planes + copy threads (RAISR_CUDA_STAGE_PAGEABLE=0 / RAISR_CUDA_COPY_THREADS=n)
@@ -285,6 +296,27 @@ struct PassPlan {
     int ups = 0;             // 0 none, 1 exact 2x, 2 axis maps
 };
 
+// Tensor map of an input plane for the pipelined kernel's stage A: 2-D, one element per sample, box = the low-res window of one
+// tile (tmap_box_w x TMAP_BOX_H), out-of-range elements zero (such tiles take the scalar path anyway).  nullptr when the plane does
+// not meet TMA's alignment rules (16-byte base and pitch) or the driver refuses: the kernel then keeps its scalar loads.
+const CUtensorMap *input_tensor_map(raisr_cuda_engine *e, const void *ptr, size_t pitch, int w, int h)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(PassParams::in_tmap), "tensor map size");
+    if ((reinterpret_cast<uintptr_t>(ptr) % 16) != 0 || (pitch % 16) != 0 || w < 1 || h < 1) return nullptr;
+    for (auto &t : e->tmaps)
+        if (t.ptr == ptr && t.pitch == pitch && t.w == w && t.h == h) return &t.map;
+    raisr_cuda_engine::TmapEntry &t = e->tmaps[e->tmap_next];
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h}, strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)(e->bps == 1 ? TmapBox<uint8_t>::W : TmapBox<uint16_t>::W), (cuuint32_t)TMAP_BOX_H}, estr[2] = {1, 1};
+    const CUresult rc = e->encode_tiled(&t.map, e->bps == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(ptr), dims,
+                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { t.ptr = nullptr; return nullptr; }
+    t.ptr = ptr; t.pitch = pitch; t.w = w; t.h = h;
+    e->tmap_next = (e->tmap_next + 1) % 4;
+    return &t.map;
+}
+
 PassPlan plan_pass(raisr_cuda_engine *e, const PassParams &p)
 {
     // tile height: the largest even th <= the kernel's maximum whose tile count still fits the same number of waves (one CTA per SM)
@@ -324,6 +356,13 @@ PassPlan plan_pass(raisr_cuda_engine *e, const PassParams &p)
     // 2x fast path: exact factor 2 in both axes and even band origin
     const bool fast2x = p.upscale && p.W == 2 * p.in_w && p.denx == 4 && p.deny == 4 && (p.row0 % 2) == 0 && p.up_src_h * 2 == p.H;
     pl.ups = !p.upscale ? 0 : (fast2x ? 1 : 2);
+    q.use_tmap = 0;
+    if (e->use_pipe && pl.ups == 1 && e->use_tma && e->encode_tiled) {
+        if (const CUtensorMap *m = input_tensor_map(e, p.in, p.in_pitch, p.in_w, p.in_h)) {
+            memcpy(q.in_tmap, m, sizeof(CUtensorMap));
+            q.use_tmap = 1;
+        }
+    }
     return pl;
 }
 
@@ -609,6 +648,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *c = std::getenv("RAISR_CUDA_CHAIN")) e->chain_passes = std::atoi(c) != 0 ? 1 : 0;
     if (const char *c = std::getenv("RAISR_CUDA_TEST_DROP_IN_FLAG")) e->test_drop_in_flag = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
+    if (const char *c = std::getenv("RAISR_CUDA_TMA")) e->use_tma = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));
     {
         int coop = 0;
@@ -728,6 +768,11 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         fn = nullptr;
         if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             e->write_value32 = reinterpret_cast<raisr_cuda_engine::WaitValue32Fn>(fn);
+        else
+            cudaGetLastError();
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            e->encode_tiled = reinterpret_cast<raisr_cuda_engine::EncodeTiledFn>(fn);
         else
             cudaGetLastError();
     }

@@ -89,7 +89,16 @@ struct PassParams {
     // Part of the launch parameters (constant bank 0, read as uniform operands): per launch, hence per engine -- engines with
     // different bit depths on one device cannot disturb each other.
     alignas(8) float gw[11][6];
+    // Pipelined kernel, exact-2x passes: CUtensorMap (opaque, 128 bytes) of the input plane, box = one tile's low-res window; stage A
+    // of interior tiles fetches it with ONE cp.async.bulk.tensor (TMA) instead of ~2000 clamped scalar loads.  use_tmap = 0: scalar path.
+    alignas(64) unsigned char in_tmap[128];
+    int use_tmap;
 };
+constexpr int TMAP_BOX_H = 31;                                       // rows of the box: (PTH_MAX + 14) / 2 + 1 of the pipelined kernel
+// box width: the window's first column is rounded down to a 16-byte boundary (TMA faults on a box whose first element is not 16-byte
+// aligned in memory -- measured: "illegal instruction" for uint8 at column 100, fine at 96), so LRW (66) + up to 15 (uint8) / 7 (uint16)
+// elements, rounded up to a multiple of 16 bytes
+template <typename PixT> struct TmapBox { static constexpr int W = sizeof(PixT) == 1 ? 96 : 80, ALIGN = 16 / (int)sizeof(PixT); };
 
 // ---- tile geometry -------------------------------------------------------------------------------
 constexpr int NT = 512;          // threads per CTA (one CTA per SM: the filter slice alone is 110 KB)
@@ -433,6 +442,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 2-D tensor-map load (TMA): box at element coordinates (c0, c1) of the plane described by *tmap -> shared memory, completion on bar
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, void *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -62,6 +62,9 @@ constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * 2 * QCHUNK;          // fi
 constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(((PTH_MAX + 14) / 2 + 1) * LRP <= PHH * HP, "low-res staging fits in the HR tile");
+// TMA landing zone of stage A's low-res window (raw samples): 128-byte aligned, in the HR tile behind the float staging above
+constexpr size_t POFF_TMA = (POFF_HR + sizeof(float) * ((PTH_MAX + 14) / 2 + 1) * LRP + 127) & ~(size_t)127;
+static_assert(POFF_TMA + 80 * 2 * TMAP_BOX_H <= POFF_HR + sizeof(float) * PHH * HP && (PTH_MAX + 14) / 2 + 1 == TMAP_BOX_H, "TMA box fits in the HR tile");
 
 // (barrier number and thread count are IMMEDIATES: the count is part of the instruction, which is also what lets
 // compute-sanitizer's synccheck see that these are partial barriers and not a __syncthreads() some threads skip)
@@ -351,6 +354,7 @@ struct PipeCarry {
     int total_iters;         // tiles this CTA walks in the whole launch (all passes)
     unsigned gk;             // producers: running chunk number (chain buffer = gk & 1)
     unsigned nload;          // filter warps: filter-slice loads issued so far (mbarrier phase)
+    unsigned ntma;           // filter warps: tensor-map loads of the low-res input window issued so far (mbarrier phase)
 };
 
 // Tiles of a pass and this CTA's first one.  A launch walks the tiles of pass A and then those of pass B as ONE round-robin
@@ -741,10 +745,32 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             float *sL = sHR;
             const int ly0 = (y0 - 8) >> 1, lx0 = (x0 - 8) >> 1;
             const int lrh = (th + 14) / 2 + 1;
-            for (int idx = ct; idx < lrh * LRW; idx += NCT) {
-                const int ly = idx / LRW, lx = idx - ly * LRW;
-                const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
-                sL[ly * LRP + lx] = (float)((unsigned)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx] >> p.in_shift);
+            // Interior tiles (no clamped coordinate; never the chained second pass, whose input the SAME launch writes through the
+            // generic proxy): the low-res window arrives by one TMA tensor-map load into the unused upper part of the HR tile and is
+            // converted from there.  Tiles on the frame border keep the clamped scalar loads (TMA fills out-of-range elements with
+            // zeros, the reference replicates the border).
+            constexpr int BW = TmapBox<PixT>::W;
+            const bool tma_tile = !DEP && p.use_tmap && lx0 >= 0 && ly0 >= 0 && lx0 + LRW <= p.in_w && ly0 + lrh <= p.up_src_h;
+            if (tma_tile) {
+                PixT *stage = reinterpret_cast<PixT *>(smem_raw + POFF_TMA);
+                if (ct == 0) {
+                    fence_proxy_async();                                  // the HR tile was last written through the generic proxy
+                    mbar_expect_tx(mslice + 1, (unsigned)(BW * TMAP_BOX_H * sizeof(PixT)));
+                    tma_load_2d(stage, p.in_tmap, lx0 & ~(TmapBox<PixT>::ALIGN - 1), ly0, mslice + 1);
+                }
+                const int xoff = lx0 & (TmapBox<PixT>::ALIGN - 1);
+                mbar_wait(mslice + 1, cy.ntma & 1u);
+                ++cy.ntma;
+                for (int idx = ct; idx < lrh * LRW; idx += NCT) {
+                    const int ly = idx / LRW, lx = idx - ly * LRW;
+                    sL[ly * LRP + lx] = (float)((unsigned)stage[ly * BW + xoff + lx] >> p.in_shift);
+                }
+            } else {
+                for (int idx = ct; idx < lrh * LRW; idx += NCT) {
+                    const int ly = idx / LRW, lx = idx - ly * LRW;
+                    const int yy = min(max(ly0 + ly, 0), p.up_src_h - 1), xx = min(max(lx0 + lx, 0), p.in_w - 1);
+                    sL[ly * LRP + lx] = (float)((unsigned)reinterpret_cast<const PixT *>(static_cast<const char *>(p.in) + (size_t)yy * p.in_pitch)[xx] >> p.in_shift);
+                }
             }
             group_sync(BAR_CONS, NCT);
             for (int idx = ct; idx < (lrh - 1) * (LRW - 1); idx += NCT) {
@@ -1063,6 +1089,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_c
         smem_raw[POFF_HASH + (size_t)(i / (HP - HW)) * HP + HW + i % (HP - HW)] = 255;
     if (tid0 == 0) {
         mbar_init(mslice, 1);
+        mbar_init(mslice + 1, 1);                                           // tensor-map loads of stage A
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1074,7 +1101,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_c
     const int nA = (tA > b) ? (tA - b + G - 1) / G : 0;
     const int tileB0 = b + nA * G - tA;                                   // first tile of pass B for this CTA (>= 0)
     const int nB = (tB > tileB0) ? (tB - tileB0 + G - 1) / G : 0;
-    PipeCarry cy{0, nA + nB, 0u, 0u};
+    PipeCarry cy{0, nA + nB, 0u, 0u, 0u};
 
     // warps [0, NCW) are the filter warps, warps [NCW, NCW + NPW) the producers (bucket warps, then chain warps)
     if (tid0 >= NCT) {
