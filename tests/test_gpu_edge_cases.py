@@ -204,3 +204,41 @@ def test_semiplanar_device_frames_equal_planar_frames(folder, ratio, bits, passe
         assert (gy & ((1 << shift) - 1)).max() == 0 and (guv & ((1 << shift) - 1)).max() == 0, "low bits must stay clear"
     assert np.array_equal(gy >> shift, py), "Y differs on %d px" % ((gy >> shift) != py).sum()
     assert np.array_equal(guv[:, 0::2] >> shift, pu) and np.array_equal(guv[:, 1::2] >> shift, pv), "chroma differs"
+
+
+@pytest.mark.parametrize("bits", [8, 10])
+def test_tma_staged_input_equals_scalar_staging(bits):
+    """Stage A of exact-2x passes fetches the low-res window of interior tiles by a tensor-map TMA load (16-byte aligned planes); frame
+    border tiles, unaligned planes and RAISR_CUDA_TMA=0 use clamped scalar loads.  All three must give the same frame -- and it must be
+    the oracle's.  (A device plane whose base is off by 2 bytes / whose pitch is not a multiple of 16 exercises the fallback.)"""
+    import torch
+    w, h = 640, 360                                      # 12 x 16 tiles of which the inner ones take the TMA path
+    f = T.filter_folder("filters_2x/filters_lowres")
+    img = T.synth_frame(w, h, bits, seed=77, kind="mix")
+    tdt = torch.uint8 if bits == 8 else torch.int16
+    bps = 1 if bits == 8 else 2
+    src = torch.from_numpy(img if bits == 8 else img.view(np.int16)).cuda()
+    outs = {}
+    for name, env, shift in (("tma", None, 0), ("scalar", "0", 0), ("unaligned", None, 2 // bps)):
+        if env is None:
+            os.environ.pop("RAISR_CUDA_TMA", None)
+        else:
+            os.environ["RAISR_CUDA_TMA"] = env
+        try:
+            eng = B.Engine(f, 2.0, bits, T.VideoRange, 1, 1, numerics=NUM)
+        finally:
+            os.environ.pop("RAISR_CUDA_TMA", None)
+        eng.set_res(w, h, 2 * w, 2 * h)
+        pitch_el = w + 32 + shift                            # elements per row of the padded device plane (a multiple of 16 bytes iff shift == 0)
+        buf = torch.zeros((h + 1) * pitch_el + 64, dtype=tdt, device="cuda")
+        plane = buf[shift:shift + h * pitch_el].view(h, pitch_el)[:, :w]
+        plane.copy_(src)
+        out = torch.empty((2 * h, 2 * w), dtype=tdt, device="cuda")
+        assert eng.process_device_rows(plane.data_ptr(), pitch_el * bps, out.data_ptr(), out.stride(0) * bps, 0, 2 * h, 2, None) == 0
+        torch.cuda.synchronize()
+        outs[name] = out.cpu().numpy()
+        eng.close()
+    ref = oracle_run(f, img, 2.0, bits)
+    for name, o in outs.items():
+        got = o if bits == 8 else o.view(np.uint16)
+        assert np.array_equal(got, ref), name
