@@ -118,6 +118,9 @@ template <int N, typename F> __device__ __forceinline__ void static_for(F &&f) {
 #ifndef RAISR_STAGE_D_SLIDE
 #define RAISR_STAGE_D_SLIDE 1
 #endif
+#ifndef RAISR_STAGE_D_WALKS
+#define RAISR_STAGE_D_WALKS 1
+#endif
 static __constant__ unsigned c_slide_tbl[8] = {0x0a521452u, 0x1a3b043bu, 0x12e40ce4u, 0x168d088du, 0x15760b76u, 0x051f1b1fu, 0x0dc013c0u, 0x09a917a9u};
 
 // Half-precision pairs of the opt-in fp16 filter stage: IEEE binary16, round to nearest even (HMUL2 / HFMA2: one rounding per
@@ -951,14 +954,15 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             const int nseg = ((hh - hs0 + 1) / 2 + 7) / 8;                // walks are cut into items of 8 steps (two units of 4)
             const unsigned lastrow_s = (unsigned)p.nbuckets - 1u;
             const unsigned fbm = fbase - 128u;
-            auto slide_item = [&](auto twoc, const int h0, const int jc0) {
-                constexpr bool TWO = decltype(twoc)::value;
-                constexpr int NSTEP = TWO ? 8 : 4;
-                unsigned ubv = smem_u32(sS) + 4u * (unsigned)(h0 * SP + jc0);       // strip origin of this item (uniform, but wanted in a vector register:
+            // A walk = nunits units (4 steps each) of one column block, starting at tile row h0; the 8-step cycle below repeats with the
+            // ring carried across cycle boundaries (CONT: step 7 also requests what step 0 of the next cycle needs -- pair 18 = pair 7
+            // of the next cycle, the coefficient units and the bucket of its first two steps -- before the bases move on by 16 rows).
+            auto slide_walk = [&](const int h0, const int jc0, int nunits) {
+                unsigned ubv = smem_u32(sS) + 4u * (unsigned)(h0 * SP + jc0);       // strip origin of this walk (uniform, but wanted in a vector register:
                 asm volatile("" : "+r"(ubv));                                      //  one add per patch load instead of a uniform-to-vector move plus a multiply-add)
-                const unsigned hva = smem_u32(sHash) + (unsigned)(g * JS + h0 * HP + jc0);
-                const unsigned hul = smem_u32(sHash) + hlane + (unsigned)(h0 * HP + jc0);
-                const unsigned hra = hrlane + 4u * (unsigned)(h0 * HP + jc0);
+                unsigned hva = smem_u32(sHash) + (unsigned)(g * JS + h0 * HP + jc0);
+                unsigned hul = smem_u32(sHash) + hlane + (unsigned)(h0 * HP + jc0);
+                unsigned hra = hrlane + 4u * (unsigned)(h0 * HP + jc0);
                 float Wx[11], Wy[11];
                 f32x2 C[16];                                                      // coefficient units: step n uses C[8 (n & 1) + 0..7], the other half is being loaded
                 float v[4];
@@ -979,50 +983,78 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 unsigned hvc = lds_u8<0>(hva), hvn = lds_u8<2 * HP>(hva);           // buckets of steps 0 and 1
                 static_for<8>([&](auto sc) { ldw(sc, std::integral_constant<int, 0>{}); });
                 ldc(std::integral_constant<int, 0>{}, fbm + (min(hvc, lastrow_s) << 9));
-                static_for<NSTEP>([&](auto nc) {
-                    constexpr int n = decltype(nc)::value;
-                    constexpr int B = 11 * n / 8, t = (3 * n) % 8, u = n & 3, cb0 = 8 * (n & 1);
-                    constexpr bool more = n + 1 < NSTEP;
-                    constexpr int tn = (3 * (n + 1)) % 8;
-                    unsigned hu = 255u;
-                    if constexpr (more) {
-                        // everything step n + 1 needs is requested before the arithmetic of step n: the pairs entering its window (their ring
-                        // slots are dead at step n), its coefficient units (other half of C), and the bucket of step n + 2
-                        constexpr int Lc = (n == 0) ? 7 : B + 8, Ln = 11 * (n + 1) / 8 + 8;
-                        static_for<Ln - Lc>([&](auto ic) {
-                            constexpr int i = Lc + 1 + decltype(ic)::value;
-                            ldw(std::integral_constant<int, i % 11>{}, std::integral_constant<int, (i >= 11) ? 16 * SP * 4 : 0>{});
+                auto cycle = [&](auto twoc, auto contc) {
+                    constexpr bool TWO = decltype(twoc)::value, CONT = decltype(contc)::value;
+                    constexpr int NSTEP = TWO ? 8 : 4;
+                    static_assert(TWO || !CONT, "a walk continues after full cycles only");
+                    static_for<NSTEP>([&](auto nc) {
+                        constexpr int n = decltype(nc)::value;
+                        constexpr int B = 11 * n / 8, t = (3 * n) % 8, u = n & 3, cb0 = 8 * (n & 1);
+                        constexpr bool more = n + 1 < NSTEP || CONT;
+                        constexpr int tn = (3 * (n + 1)) % 8;
+                        unsigned hu = 255u;
+                        if constexpr (more) {
+                            // everything step n + 1 needs is requested before the arithmetic of step n: the pairs entering its window (their ring
+                            // slots are dead at step n), its coefficient units (other half of C), and the bucket of step n + 2
+                            constexpr int Lc = (n == 0) ? 7 : B + 8, Ln = (n == 7) ? 18 : 11 * (n + 1) / 8 + 8;
+                            static_for<Ln - Lc>([&](auto ic) {
+                                constexpr int i = Lc + 1 + decltype(ic)::value;
+                                ldw(std::integral_constant<int, i % 11>{}, std::integral_constant<int, (i >= 11) ? 16 * SP * 4 : 0>{});
+                            });
+                            ldc(std::integral_constant<int, (n + 1) & 7>{}, fbm + (min(hvn, lastrow_s) << 9) + ((q < tn) ? 128u : 0u));
+                            if constexpr (n + 2 < NSTEP || CONT) hvn = lds_u8<2 * HP * (n + 2)>(hva);
+                        }
+                        if constexpr (u == 3) hu = lds_u8<2 * HP * (n - 3)>(hul);   // bucket of the pixel this lane ends up with
+                        f32x2 aU = 0ull, aF = 0ull;
+                        static_for<8>([&](auto mc) {
+                            constexpr int m = decltype(mc)::value;
+                            const f32x2 wu = pack2(Wx[(B + m) % 11], Wy[(B + m) % 11]);
+                            aU = (m == 0) ? mul2(wu, C[cb0 + m]) : fma2(wu, C[cb0 + m], aU);
+                            if constexpr (t != 0) {
+                                const f32x2 wf = pack2(Wx[(B + 1 + m) % 11], Wy[(B + 1 + m) % 11]);
+                                aF = (m == 0) ? mul2(wf, C[cb0 + m]) : fma2(wf, C[cb0 + m], aF);
+                            }
                         });
-                        ldc(std::integral_constant<int, n + 1>{}, fbm + (min(hvn, lastrow_s) << 9) + ((q < tn) ? 128u : 0u));
-                        if constexpr (n + 2 < NSTEP) hvn = lds_u8<2 * HP * (n + 2)>(hva);
-                    }
-                    if constexpr (u == 3) hu = lds_u8<2 * HP * (n - 3)>(hul);       // bucket of the pixel this lane ends up with
-                    f32x2 aU = 0ull, aF = 0ull;
-                    static_for<8>([&](auto mc) {
-                        constexpr int m = decltype(mc)::value;
-                        const f32x2 wu = pack2(Wx[(B + m) % 11], Wy[(B + m) % 11]);
-                        aU = (m == 0) ? mul2(wu, C[cb0 + m]) : fma2(wu, C[cb0 + m], aU);
-                        if constexpr (t != 0) {
-                            const f32x2 wf = pack2(Wx[(B + 1 + m) % 11], Wy[(B + 1 + m) % 11]);
-                            aF = (m == 0) ? mul2(wf, C[cb0 + m]) : fma2(wf, C[cb0 + m], aF);
+                        float a0, a1;
+                        if constexpr (t != 0) unpack2((q < t) ? aF : aU, a0, a1); else unpack2(aU, a0, a1);
+                        const bool hi = ((stbl >> (16 * (n >> 2) + 9 + u)) & 1u) != 0u;
+                        v[u] = fadd(hi ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 4, 8));
+                        if constexpr (u == 3) {
+                            constexpr int SH0 = 16 * (n >> 2), n0 = n - 3;
+                            const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+                            const float w0 = fadd(b1 ? v[2] : v[0], __shfl_sync(0xffffffffu, b1 ? v[0] : v[2], (int)(stbl >> SH0), 8));
+                            const float w1 = fadd(b1 ? v[3] : v[1], __shfl_sync(0xffffffffu, b1 ? v[1] : v[3], (int)(stbl >> (SH0 + 3)), 8));
+                            const float x = fadd(b0 ? w1 : w0, __shfl_sync(0xffffffffu, b0 ? w0 : w1, (int)(stbl >> (SH0 + 6)), 8));
+                            const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));
+                            if (q < 4 && hu != 255u && cur > flo && cur < fhi) sts_f32(hra + 4u * (unsigned)(2 * n0 * HP), cur);
                         }
                     });
-                    float a0, a1;
-                    if constexpr (t != 0) unpack2((q < t) ? aF : aU, a0, a1); else unpack2(aU, a0, a1);
-                    const bool hi = ((stbl >> (16 * (n >> 2) + 9 + u)) & 1u) != 0u;
-                    v[u] = fadd(hi ? a1 : a0, __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 4, 8));
-                    if constexpr (u == 3) {
-                        constexpr int SH0 = 16 * (n >> 2), n0 = n - 3;
-                        const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
-                        const float w0 = fadd(b1 ? v[2] : v[0], __shfl_sync(0xffffffffu, b1 ? v[0] : v[2], (int)(stbl >> SH0), 8));
-                        const float w1 = fadd(b1 ? v[3] : v[1], __shfl_sync(0xffffffffu, b1 ? v[1] : v[3], (int)(stbl >> (SH0 + 3)), 8));
-                        const float x = fadd(b0 ? w1 : w0, __shfl_sync(0xffffffffu, b0 ? w0 : w1, (int)(stbl >> (SH0 + 6)), 8));
-                        const float cur = fadd(x, __shfl_xor_sync(0xffffffffu, x, 4, 8));
-                        if (q < 4 && hu != 255u && cur > flo && cur < fhi) sts_f32(hra + 4u * (unsigned)(2 * n0 * HP), cur);
-                    }
-                });
+                };
+                while (nunits > 2) {
+                    cycle(std::true_type{}, std::true_type{});
+                    ubv += 16u * SP * 4u; hva += 16u * HP; hul += 16u * HP; hra += 4u * 16u * HP;
+                    nunits -= 2;
+                }
+                if (nunits == 2) cycle(std::true_type{}, std::false_type{});
+                else cycle(std::false_type{}, std::false_type{});
             };
-            // items in segment-major order: the divisor of the index split is a compile-time constant
+#if RAISR_STAGE_D_WALKS
+            // Work = units of 4 steps in column-major order; every filter warp takes one contiguous range (7 or 8 of the 90 units of a
+            // pixel type at 4K), i.e. one or two whole columns' worth: a window start-up per column crossing instead of one per 8 steps.
+            constexpr int NCI = NCB * NWALK;
+            const int nunit = ((hh - hs0 + 1) / 2 + 3) / 4;                   // units per walk
+            const int nu_total = NCI * nunit;
+            const int u_begin = nu_total * cwarp / NCW, u_end = nu_total * (cwarp + 1) / NCW;
+            for (int uu = u_begin; uu < u_end;) {
+                const int cw = uu / nunit, ua = uu - cw * nunit;
+                const int cnt = min(nunit - ua, u_end - uu);
+                const int wk = (NWALK == 2) ? (cw & 1) : 0, cb = (NWALK == 2) ? (cw >> 1) : cw;
+                const int h0 = hs0 + wk + 8 * ua, jc0 = jfirst + 4 * cb * JS;
+                if (x0 - 1 + jc0 < p.c_end) slide_walk(h0, jc0, cnt);
+                uu += cnt;
+            }
+#else
+            // items of (at most) two units in segment-major order: the divisor of the index split is a compile-time constant
             constexpr int NCI = NCB * NWALK;
             for (int it = cwarp; it < NCI * nseg; it += NCW) {
                 const int sg = it / NCI, cw = it - sg * NCI;
@@ -1031,9 +1063,9 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
                 const int left = (hh - hsw + 1) / 2 - 8 * sg;             // steps left in this walk
                 const int h0 = hsw + 16 * sg, jc0 = jfirst + 4 * cb * JS;
                 if (left <= 0 || x0 - 1 + jc0 >= p.c_end) continue;
-                if (left > 4) slide_item(std::true_type{}, h0, jc0);
-                else slide_item(std::false_type{}, h0, jc0);
+                slide_walk(h0, jc0, left > 4 ? 2 : 1);
             }
+#endif
             }
             // Columns hashed by both the 16-wide and the 8-wide variant (Raisr.cpp:1246-1250): the pass above used the 8-wide
             // bucket (the later evaluation); where that result was out of range the reference keeps the 16-wide evaluation.
