@@ -321,6 +321,7 @@ struct HashCtx {
     float quarter, half;     // X86 8-wide hash: Newton-refined rcpps(4), rcpps(2)
     const unsigned *rsqrt14, *rcp14;       // shared memory: packed, replicated 14-bit instruction tables, this lane's replica
     const uint16_t *rsqrtps, *rcpps;       // global (row tails only)
+    float fnangles;          // (float)nangles
 };
 
 // atan2 approximation, Raisr_AVX512.cpp:151-173 (== Raisr_AVX256.cpp:366-391), given the quotient q
@@ -335,7 +336,7 @@ __device__ __forceinline__ int quantise(const HashCtx &h, bool wide16, float ang
 {
     ang = fadd(ang, (ang < 0.0f) ? 3.141592653f : 0.0f);                       // PI, Raisr_globals.h:29
     const float fa = floorf(fmul(ang, h.qangle));
-    const int ai = (fa >= 0.0f) ? ((fa < (float)h.nangles) ? (int)fa : h.nangles - 1) : 0;   // NaN -> INT_MIN -> max(.,0) = 0
+    const int ai = (fa >= 0.0f) ? ((fa < h.fnangles) ? (int)fa : h.nangles - 1) : 0;   // NaN -> INT_MIN -> max(.,0) = 0
     int si, ci;
     if (wide16) {            // thresholds <= value, NaN -> 0   (Raisr_AVX512.cpp:242-249)
         si = (h.qstr0 <= str) + (h.qstr1 <= str);
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     __syncthreads();
 
     HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
-               p.lut_rsqrtps, p.lut_rcpps};
+               p.lut_rsqrtps, p.lut_rcpps, (float)p.nangles};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 
     for (int h0 = 0; h0 < hh; h0 += RB) {

@@ -413,7 +413,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
     const int gx = (W + TW - 1) / TW;
     const int ntiles = pass_tiles(p);
     HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
-               p.lut_rsqrtps, p.lut_rcpps};
+               p.lut_rsqrtps, p.lut_rcpps, (float)p.nangles};
 
     // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
     // Y = y0-7+s odd = 2j+1 and s+1 <-> 2j+2: both interpolate low-res rows (j, j+1) with weights (3,1) / (1,3); likewise the
@@ -520,10 +520,14 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
         };
         // ---- C: bucket of chunk kc, one pixel per thread <- sQ[kc & 1].  The 16-wide hash runs unconditionally (garbage in,
         // nothing stored, for threads without a hashed pixel); only the row-tail columns take the 8-wide branch.
+        // what depends on the thread's column only: decided once per tile, not once per chunk
+        const int cj = min(q, HW - 1), cc = x0 - 1 + cj;
+        const bool col_hashed = cc >= 6 && cc < p.c_end, col_tail = cc >= p.tail_start, col_both = cc < p.ov_end;
+        const bool col_ov = cc >= p.tail_start && cc < p.tail_start + OVW, col_out = p.hash_out != nullptr && cj >= 1 && cj <= TW;
         auto stage_C = [&](int kc) {
             const int h = RBP * kc + rl;
-            const int j = min(q, HW - 1);
-            const int r = y0 - 1 + h, c = x0 - 1 + j;
+            const int j = cj;
+            const int r = y0 - 1 + h, c = cc;
             float g[3];
             const float *qs = sQ + ((gk + kc) & 1u) * QCHUNK + (rl * 18) * QW + j;
 #pragma unroll
@@ -543,18 +547,18 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                     g[k3] = tree_sum(lane);
                 }
             }
-            const bool hashed = r >= 6 && r < H - 6 && c >= 6 && c < p.c_end;
+            const bool hashed = col_hashed && r >= 6 && r < H - 6;
             int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
-            if (hashed && c >= p.tail_start) {
+            if (hashed && col_tail) {
                 const int h8 = hash_bucket<false>(hc, g[0], g[1], g[2]);
-                if (c < p.ov_end && hv != h8) hv2 = hv;         // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
+                if (col_both && hv != h8) hv2 = hv;             // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
                 hv = h8;
             }
             if (!hashed) hv = 255;
             if (q < HW && h < hh) {
-                if (p.hash_out && hashed && r >= p.row0 && r < p.row1 && j >= 1 && j <= TW) p.hash_out[(size_t)r * W + c] = hv;
+                if (col_out && hashed && r >= p.row0 && r < p.row1) p.hash_out[(size_t)r * W + c] = hv;
                 sHash[h * HP + j] = (unsigned char)hv;
-                if (c >= p.tail_start && c < p.tail_start + OVW) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
+                if (col_ov) sHash2[h * OVW + (c - p.tail_start)] = (unsigned char)hv2;
             }
         };
         const int nchunks = hh / RBP;
