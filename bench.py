@@ -618,7 +618,7 @@ def main():
             "e2e_pageable": {"value": e2e_pageable, "unit": "frames/s", "api": "RNLHandler_Process, pageable host planes (malloc)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "raisr_frame_pipe_kernel<uint8_t,4,1,-1,0>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "raisr_frame_pipe_kernel<uint8_t,4,1,-1,%d>" % (4 if numerics == 1 else 0), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_Y,
                          "note": "on-chip bound stencil (shared-memory pipe + issue slots), see DESIGN.md section 4"},

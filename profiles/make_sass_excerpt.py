@@ -2,8 +2,8 @@
 usage: python profiles/make_sass_excerpt.py"""
 import collections, os, re, subprocess
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-OBJ = os.path.join(ROOT, "video-super-resolution-library_b200", "build", "raisr_pipe_u8.o")
-FUN = "_ZN5raisr23raisr_frame_pipe_kernelIhLi4ELi1ELin1ELi0EEEvNS_10PassParamsES1_"
+OBJ = os.path.join(ROOT, "video-super-resolution-library_b200", "build", "raisr_pipe_u8x.o")
+FUN = "_ZN5raisr23raisr_frame_pipe_kernelIhLi4ELi1ELin1ELi4EEEvNS_10PassParamsES1_"
 raw = subprocess.run(["cuobjdump", "-sass", "-fun", FUN, OBJ], capture_output=True, text=True).stdout
 L = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/", "", l).rstrip() for l in raw.splitlines() if re.match(r"^\s+/\*[0-9a-f]{4,5}\*/", l)]
 ops = collections.Counter()
@@ -20,8 +20,8 @@ def find(pat, start=0):
     return -1
 
 
-out = ["SASS of the shipped hot instantiation raisr_frame_pipe_kernel<uint8_t, 4, 1, -1, 0> (1080p->4K, 8-bit, exact 2x; one pass, exact numerics)",
-       "cuobjdump -sass -fun %s video-super-resolution-library_b200/build/raisr_pipe_u8.o" % FUN,
+out = ["SASS of the shipped hot instantiation raisr_frame_pipe_kernel<uint8_t, 4, 1, -1, 4> (1080p->4K, 8-bit, exact 2x; one pass, exact numerics)",
+       "cuobjdump -sass -fun %s video-super-resolution-library_b200/build/raisr_pipe_u8x.o" % FUN,
        "(nvcc 12.9, -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo); regenerate with profiles/make_sass_excerpt.py",
        "%d instructions.  Static opcode census (whole kernel):" % len(L),
        "  " + ", ".join("%s:%d" % kv for kv in ops.most_common(26)),

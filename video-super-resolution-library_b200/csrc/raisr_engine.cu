@@ -372,11 +372,19 @@ int cuda_failed(int err, const char *what)
     return RNLErrorInsufficientResources;
 }
 
+// instantiation of the pipelined kernel (raisr_pipe_kernel.cuh "NV"): 1 fp16 filter stage, 2 separable fast hash, 4 exact with the X86
+// numerics compiled in, 0 exact with the numerics decided at run time (IEEE)
+int pipe_variant(const raisr_cuda_engine *e)
+{
+    return e->filter_fp16 ? 1 : e->fast_hash ? 2 : e->cfg.numerics == RAISR_NUMERICS_X86 ? 4 : 0;
+}
+
 int launch_frame(raisr_cuda_engine *e, const FrameLaunch &fl)
 {
-    const int nv = e->filter_fp16 ? 1 : e->fast_hash ? 2 : 0;
-    if (e->bps == 1) return nv == 1 ? launch_frame_pipe<uint8_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint8_t, 2>(fl) : launch_frame_pipe<uint8_t, 0>(fl);
-    return nv == 1 ? launch_frame_pipe<uint16_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint16_t, 2>(fl) : launch_frame_pipe<uint16_t, 0>(fl);
+    const int nv = pipe_variant(e);
+    if (e->bps == 1)
+        return nv == 1 ? launch_frame_pipe<uint8_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint8_t, 2>(fl) : nv == 4 ? launch_frame_pipe<uint8_t, 4>(fl) : launch_frame_pipe<uint8_t, 0>(fl);
+    return nv == 1 ? launch_frame_pipe<uint16_t, 1>(fl) : nv == 2 ? launch_frame_pipe<uint16_t, 2>(fl) : nv == 4 ? launch_frame_pipe<uint16_t, 4>(fl) : launch_frame_pipe<uint16_t, 0>(fl);
 }
 
 // one pass = one launch
@@ -740,9 +748,9 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
         // > 48 KB dynamic shared memory is a per-device function attribute: set for this engine's kernels on this engine's device
         int err = e->bps == 1 ? prepare_pass_tile<uint8_t>() : prepare_pass_tile<uint16_t>();
         if (!err) {
-            const int nv = e->filter_fp16 ? 1 : e->fast_hash ? 2 : 0;
-            if (e->bps == 1) err = nv == 1 ? prepare_frame_pipe<uint8_t, 1>() : nv == 2 ? prepare_frame_pipe<uint8_t, 2>() : prepare_frame_pipe<uint8_t, 0>();
-            else err = nv == 1 ? prepare_frame_pipe<uint16_t, 1>() : nv == 2 ? prepare_frame_pipe<uint16_t, 2>() : prepare_frame_pipe<uint16_t, 0>();
+            const int nv = pipe_variant(e);
+            if (e->bps == 1) err = nv == 1 ? prepare_frame_pipe<uint8_t, 1>() : nv == 2 ? prepare_frame_pipe<uint8_t, 2>() : nv == 4 ? prepare_frame_pipe<uint8_t, 4>() : prepare_frame_pipe<uint8_t, 0>();
+            else err = nv == 1 ? prepare_frame_pipe<uint16_t, 1>() : nv == 2 ? prepare_frame_pipe<uint16_t, 2>() : nv == 4 ? prepare_frame_pipe<uint16_t, 4>() : prepare_frame_pipe<uint16_t, 0>();
         }
         if (err) { cuda_failed(err, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); return fail(RNLErrorInsufficientResources); }
     }

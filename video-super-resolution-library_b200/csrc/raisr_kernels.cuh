@@ -357,12 +357,14 @@ __device__ __forceinline__ float nr_recip(float r, float den) { return fsub(fadd
 // numerics IEEE: the source semantics with sqrt.rn / div.rn (oracle: hash_bucket_ieee).
 // numerics X86 : the functions as compiled by g++ 13.3 -O3 -ffast-math (oracle: hash_bucket_x86, transcribed from the
 //                disassembly of the reference binary): contracted determinant, rcp(rsqrt()) roots, rcp+Newton divisions.
-template <bool WIDE16>
+// NUMK: numerics known at compile time (1: X86, the IEEE code is not even instantiated -- no out-of-line sqrt / division calls in the
+// bucket warps' loop, which lets ptxas keep the hash constants in uniform registers) or -1: decided by h.numerics at run time.
+template <bool WIDE16, int NUMK = -1>
 __device__ __forceinline__ int hash_bucket(const HashCtx &h, float a, float b, float d)
 {
     const float T = fadd(a, d);
     const float ay = fadd(fabsf(b), 1e-10f);
-    if (h.numerics == 0) {
+    if (NUMK < 0 ? (h.numerics == 0) : (NUMK == 0)) {
         const float D = fsub(fmul(a, d), fmul(b, b));
         const float s = __fsqrt_rn(fsub(fmul(fmul(T, T), 0.25f), D));
         const float hT = fmul(T, 0.5f);
@@ -496,10 +498,11 @@ __device__ __forceinline__ float dot8(const float *sp, const float *frow, const 
 //             the integer upscale itself (Raisr.cpp:999-1028,1252-1265).
 // blending 1: Randomness (Raisr.cpp:1203-1242, CTRandomness_AVX512_32f Raisr_AVX512.cpp:19-35) on hashed pixels only,
 //             everything else is the integer upscale (border memcpys).
-template <typename PixT, int BL>
+template <typename PixT, int BL, int NUMK = -1>
 __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
                                                   int x0, int y0, int th, int t0, int nthreads)
 {
+    const bool ieee = NUMK < 0 ? (p.numerics == 0) : (NUMK == 0);
     const int W = p.W, H = p.H;
     for (int idx = t0; idx < th * (TW / 4); idx += nthreads) {
         const int ty = idx / (TW / 4), tx = (idx - ty * (TW / 4)) * 4;
@@ -529,7 +532,7 @@ __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const f
                     }
                 const float w = fmul((float)ham, 0.125f);
                 // source semantics: (w*LR + (1-w)*HR) + 0.5; as compiled (-ffast-math): fma(1-w, HR, fma(LR, w, 0.5)), one rounding
-                const float v = (p.numerics == 0) ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
+                const float v = ieee ? fadd(fadd(fmul(w, lc), fmul(fsub(1.0f, w), hcv)), 0.5f)
                                                   : ffma(fsub(1.0f, w), hcv, ffma(lc, w, 0.5f));
                 r = min(max((int)floorf(v), p.lo), p.hi);
                 if (Y == 0 || Y == H - 1 || X + e == 0 || X + e == W - 1) r = (int)lc;   // 1-px frame
@@ -544,7 +547,7 @@ __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const f
                     }
                 const float w = fmul((float)census, 0.125f), w2 = fsub(1.0f, w);
                 // source: w*cur + (1-w)*LR, += 0.5; as compiled: fma(w, cur, (1-w)*LR) then + 0.5   (hcv = this pixel's cur)
-                const float v = fadd((p.numerics == 0) ? fadd(fmul(w, hcv), fmul(w2, lc)) : ffma(w, hcv, fmul(w2, lc)), 0.5f);
+                const float v = fadd(ieee ? fadd(fmul(w, hcv), fmul(w2, lc)) : ffma(w, hcv, fmul(w2, lc)), 0.5f);
                 r = (v < (float)p.lo) ? p.lo : ((v > (float)p.hi) ? p.hi : (int)v);
                 if (sHash[(ty + 1) * HP + tx + 1 + e] == 255) r = (int)lc;               // not hashed: border copy of the upscale
             }
@@ -563,12 +566,12 @@ __device__ __forceinline__ void stage_blend_store_t(const PassParams &p, const f
     }
 }
 
-template <typename PixT>
+template <typename PixT, int NUMK = -1>
 __device__ __forceinline__ void stage_blend_store(const PassParams &p, const float *sS, const float *sHR, const unsigned char *sHash,
                                                   int x0, int y0, int th, int t0, int nthreads)
 {
-    if (p.blending == 2) stage_blend_store_t<PixT, 2>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
-    else stage_blend_store_t<PixT, 1>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
+    if (p.blending == 2) stage_blend_store_t<PixT, 2, NUMK>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
+    else stage_blend_store_t<PixT, 1, NUMK>(p, sS, sHR, sHash, x0, y0, th, t0, nthreads);
 }
 
 // UPS: 0 = the pass does not upscale, 1 = exact 2x (weights {1/4,3/4}^2 from a low-res tile in shared memory),

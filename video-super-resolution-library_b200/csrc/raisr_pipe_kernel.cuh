@@ -400,7 +400,7 @@ static __device__ __noinline__ void wait_rows_done(const unsigned *done, unsigne
 // of its literals (|w[i][k] - a[i] a[k]| <= 2.3e-6 w[i][k], a[i] = sqrt(w[i][i])), so GTWG = sum_i sum_k w[i][k] g g can run as an
 // 11-tap vertical pass (stage B: 3 values per position instead of 18 chains) and an 11-tap horizontal pass (stage C).  ~70 instead
 // of ~230 flops per pixel -- and other roundings: buckets are no longer bit-identical to the reference (measured agreement: DESIGN.md).
-template <typename PixT, int PT, int UPS, bool DEP, bool FASTH>
+template <typename PixT, int PT, int UPS, bool DEP, bool FASTH, int NUMK>
 __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int tid)
 {
     const float (&gw)[6][6] = (sizeof(PixT) == 1) ? c_gw8 : c_gw10;
@@ -548,9 +548,9 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                 }
             }
             const bool hashed = col_hashed && r >= 6 && r < H - 6;
-            int hv = hash_bucket<true>(hc, g[0], g[1], g[2]), hv2 = 255;
+            int hv = hash_bucket<true, NUMK>(hc, g[0], g[1], g[2]), hv2 = 255;
             if (hashed && col_tail) {
-                const int h8 = hash_bucket<false>(hc, g[0], g[1], g[2]);
+                const int h8 = hash_bucket<false, NUMK>(hc, g[0], g[1], g[2]);
                 if (col_both && hv != h8) hv2 = hv;             // also hashed by the 16-wide block before (kept if the 8-wide result is out of range)
                 hv = h8;
             }
@@ -638,7 +638,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
 // F16: opt-in fp16 filter stage (RAISR_NUMERICS_FP16_FILTER): the filter slice holds half-precision coefficients (half the
 // bytes per slice and per row), patch values are converted to half2 and the 16 chains run as HMUL2/HFMA2; the 16 chain sums are
 // then added in fp32 with the same tree.  Buckets are untouched (the hash stays fp32); Y is NOT bit-identical in this mode.
-template <typename PixT, int PT, int UPS, bool DEP, bool F16>
+template <typename PixT, int PT, int UPS, bool DEP, bool F16, int NUMK>
 __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned char *smem_raw, int tile0, PipeCarry &cy, int ct)
 {
     float *sS = reinterpret_cast<float *>(smem_raw + POFF_S);
@@ -1095,7 +1095,7 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             group_sync(BAR_CONS, NCT);
         }
         // ---- E: blend + store ----
-        stage_blend_store<PixT>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
+        stage_blend_store<PixT, NUMK>(p, sS, sHR, sHash, x0, y0, th, ct, NCT);
         group_sync(BAR_CONS, NCT);                                        // S / HR are rewritten by the next tile's stage A
         if (cy.iter + 2 < cy.total_iters) named_arrive_buf<BAR_EMPTY, NBT + NCT>(buf);   // bucket tile may be refilled (two tiles on, possibly in the next pass)
         if (ct == 0 && (p.band_done || p.rows_done)) {
@@ -1111,7 +1111,9 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
 // UPSA / UPSB: upscale flavour of the first / second pass of the launch (0 = none, 1 = exact 2x, 2 = axis maps); UPSB = -1: one
 // pass.  With two passes (pb.dep_done set by the host, cooperative launch: all CTAs resident) the second pass reads the plane
 // the first one writes; tile rows are handed over through pa.rows_done / pb.dep_done.
-// NV: numerics variant of the launch -- 0: exact (bit-identical to the reference), 1: fp16 filter stage, 2: separable fast hash.
+// NV: numerics variant of the launch -- 0: exact (bit-identical to the reference; IEEE or X86 numerics decided at run time), 1: fp16
+// filter stage, 2: separable fast hash, 4: exact with the X86 numerics compiled in (the default on a library with the tables: the hot
+// loops carry no IEEE code).
 template <typename PixT, int PT, int UPSA, int UPSB, int NV>
 __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_constant__ PassParams pa, const __grid_constant__ PassParams pb)
 {
@@ -1145,12 +1147,12 @@ __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_c
         // hand registers to the filter warpgroups; the chain warps (18 accumulators) need fewer than the hash
         if (tid >= NBT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS));
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BUCKET_REGS));
-        pipe_producer_pass<PixT, PT, UPSA, false, NV == 2>(pa, smem_raw, b, cy, tid);
-        if constexpr (UPSB >= 0) pipe_producer_pass<PixT, PT, UPSB, true, NV == 2>(pb, smem_raw, tileB0, cy, tid);
+        pipe_producer_pass<PixT, PT, UPSA, false, NV == 2, (NV == 4 ? 1 : -1)>(pa, smem_raw, b, cy, tid);
+        if constexpr (UPSB >= 0) pipe_producer_pass<PixT, PT, UPSB, true, NV == 2, (NV == 4 ? 1 : -1)>(pb, smem_raw, tileB0, cy, tid);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONS_REGS));
-        pipe_filter_pass<PixT, PT, UPSA, false, NV == 1>(pa, smem_raw, b, cy, tid0);
-        if constexpr (UPSB >= 0) pipe_filter_pass<PixT, PT, UPSB, true, NV == 1>(pb, smem_raw, tileB0, cy, tid0);
+        pipe_filter_pass<PixT, PT, UPSA, false, NV == 1, (NV == 4 ? 1 : -1)>(pa, smem_raw, b, cy, tid0);
+        if constexpr (UPSB >= 0) pipe_filter_pass<PixT, PT, UPSB, true, NV == 1, (NV == 4 ? 1 : -1)>(pb, smem_raw, tileB0, cy, tid0);
     }
 }
 
