@@ -1049,8 +1049,9 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             const int nunit = ((hh - hs0 + 1) / 2 + 3) / 4;                   // units per walk
             const int nu_total = NCI * nunit;
             const int u_begin = nu_total * cwarp / NCW, u_end = nu_total * (cwarp + 1) / NCW;
+            const unsigned inv_nunit = (65536u + (unsigned)nunit - 1u) / (unsigned)nunit;   // uu / nunit == (uu * inv) >> 16 for uu < 2^14 / nunit ... (uu <= 2 * NCB * 6)
             for (int uu = u_begin; uu < u_end;) {
-                const int cw = uu / nunit, ua = uu - cw * nunit;
+                const int cw = (int)(((unsigned)uu * inv_nunit) >> 16), ua = uu - cw * nunit;
                 const int cnt = min(nunit - ua, u_end - uu);
                 const int wk = (NWALK == 2) ? (cw & 1) : 0, cb = (NWALK == 2) ? (cw >> 1) : cw;
                 const int h0 = hs0 + wk + 8 * ua, jc0 = jfirst + 4 * cb * JS;
