@@ -335,17 +335,23 @@ __device__ __forceinline__ float atan_poly(float q, bool xneg, float b)
 __device__ __forceinline__ int quantise(const HashCtx &h, bool wide16, float ang, float str, float coh)
 {
     ang = fadd(ang, (ang < 0.0f) ? 3.141592653f : 0.0f);                       // PI, Raisr_globals.h:29
-    const float fa = floorf(fmul(ang, h.qangle));
-    const int ai = (fa >= 0.0f) ? ((fa < h.fnangles) ? (int)fa : h.nangles - 1) : 0;   // NaN -> INT_MIN -> max(.,0) = 0
-    int si, ci;
+    // floor, then clamp to [0, nangles - 1]; NaN -> 0 (cvt.rmi.s32.f32 saturates and turns NaN into 0): the reference's
+    // min(max(cvt(floor(.)), 0), 23) with its NaN -> INT_MIN -> 0, without a branch
+    const int ai = min(max(__float2int_rd(fmul(ang, h.qangle)), 0), h.nangles - 1);
+    int idx = ai * 9;
     if (wide16) {            // thresholds <= value, NaN -> 0   (Raisr_AVX512.cpp:242-249)
-        si = (h.qstr0 <= str) + (h.qstr1 <= str);
-        ci = (h.qcoh0 <= coh) + (h.qcoh1 <= coh);
+        idx += (h.qstr0 <= str) ? 3 : 0;
+        idx += (h.qstr1 <= str) ? 3 : 0;
+        idx += (h.qcoh0 <= coh) ? 1 : 0;
+        idx += (h.qcoh1 <= coh) ? 1 : 0;
     } else {                 // 2 - [value <= Q0] - [value <= Q1], NaN -> 2   (Raisr_AVX256.cpp:457-464)
-        si = 2 - ((str <= h.qstr0) + (str <= h.qstr1));
-        ci = 2 - ((coh <= h.qcoh0) + (coh <= h.qcoh1));
+        idx += 8;
+        idx -= (str <= h.qstr0) ? 3 : 0;
+        idx -= (str <= h.qstr1) ? 3 : 0;
+        idx -= (coh <= h.qcoh0) ? 1 : 0;
+        idx -= (coh <= h.qcoh1) ? 1 : 0;
     }
-    return ai * 9 + si * 3 + ci;
+    return idx;
 }
 
 // reciprocal approximation + one Newton step, the form g++ -ffast-math gives every division of the hash
