@@ -250,7 +250,31 @@ __host__ __device__ __forceinline__ float x86_rcp14(const uint2 *t, float x)
 // lookup instead of a 64-bit one, and two lanes can only collide when they use the same replica AND their entries differ by a
 // multiple of 8: the eight lookups per pixel took 11.6 M of the kernel's 127 M shared-memory wavefronts, 6.7 M of them bank
 // conflicts (profiles/r2_pipe_kernel_summary.txt).
+// Round 2, once the kernel had become bound by instruction issue and the bucket warps its critical path: the tables are stored
+// UNPACKED again, entry e as the pair (c0, -c1), twice (replica r = lane & 1 at words 4e + 2r): one 64-bit load and one IMAD per
+// lookup instead of a 32-bit load, two shifts / masks to unpack, a negation and the IMAD -- 4 instructions fewer per lookup, 32 per
+// pixel -- at the price of the bank conflicts the packing had removed (the shared-memory pipe has room now).  Same 4 KB.
+#ifndef RAISR_LUT_UNPACKED
+#define RAISR_LUT_UNPACKED 1
+#endif
 constexpr int LUT_WORDS = 2 * 128 * 4;         // rsqrt14 then rcp14
+#if RAISR_LUT_UNPACKED
+constexpr int LUT_REPLICA_MASK = 1, LUT_REPLICA_WORDS = 2;
+__device__ __forceinline__ unsigned lut14(const unsigned *t, unsigned entry, unsigned low9)
+{
+    const uint2 w = *reinterpret_cast<const uint2 *>(t + entry * 4u);
+    return (w.x + w.y * low9) >> 9;            // c0 - c1 * low9 (mod 2^32; the difference is never negative)
+}
+__device__ __forceinline__ void lut14_fill(unsigned *dst, const uint2 *rsqrt14, const uint2 *rcp14, int tid, int nthreads)
+{
+    for (int i = tid; i < LUT_WORDS / 2; i += nthreads) {          // pair i = (table, entry, replica)
+        const uint2 c = (i < LUT_WORDS / 4) ? rsqrt14[(i >> 1) & 127] : rcp14[(i >> 1) & 127];
+        dst[2 * i] = c.x;
+        dst[2 * i + 1] = 0u - c.y;
+    }
+}
+#else
+constexpr int LUT_REPLICA_MASK = 3, LUT_REPLICA_WORDS = 1;
 __device__ __forceinline__ unsigned lut14(const unsigned *t, unsigned entry, unsigned low9)
 {
     const unsigned w = t[entry * 4u];
@@ -263,6 +287,7 @@ __device__ __forceinline__ void lut14_fill(unsigned *dst, const uint2 *rsqrt14, 
         dst[i] = ((c.x >> 6) << 10) | c.y;
     }
 }
+#endif
 
 __device__ __forceinline__ float x86_rcp14_pos(const unsigned *t, float x)
 {
@@ -655,7 +680,7 @@ __global__ void __launch_bounds__(NT, 1) raisr_pass_kernel(const PassParams p)
     }
     __syncthreads();
 
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & LUT_REPLICA_MASK) * LUT_REPLICA_WORDS, sLut + LUT_WORDS / 2 + (tid & LUT_REPLICA_MASK) * LUT_REPLICA_WORDS,
                p.lut_rsqrtps, p.lut_rcpps, (float)p.nangles};
     const float flo = (float)p.lo, fhi = (float)p.hi;
 

@@ -412,7 +412,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
     const int W = p.W, H = p.H;
     const int gx = (W + TW - 1) / TW;
     const int ntiles = pass_tiles(p);
-    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & 3), sLut + LUT_WORDS / 2 + (tid & 3),
+    HashCtx hc{p.qstr0, p.qstr1, p.qcoh0, p.qcoh1, p.numerics, p.qangle, p.nangles, p.quarter, p.half, sLut + (tid & LUT_REPLICA_MASK) * LUT_REPLICA_WORDS, sLut + LUT_WORDS / 2 + (tid & LUT_REPLICA_MASK) * LUT_REPLICA_WORDS,
                p.lut_rsqrtps, p.lut_rcpps, (float)p.nangles};
 
     // 2x fast path: one thread = one 2x2 block of the upscaled plane from 4 low-res samples.  Ring row s even <-> frame row
