@@ -121,6 +121,11 @@ template <int N, typename F> __device__ __forceinline__ void static_for(F &&f) {
 #ifndef RAISR_STAGE_D_WALKS
 #define RAISR_STAGE_D_WALKS 1
 #endif
+// byte offset of ring row i & (RING-1) of the producers' S ring, i = 0 .. 2 RING - 1 (stage B: window rows by uniform table look-up)
+static __constant__ int c_ringoff[32] = {0 * 568, 1 * 568, 2 * 568, 3 * 568, 4 * 568, 5 * 568, 6 * 568, 7 * 568, 8 * 568, 9 * 568, 10 * 568, 11 * 568,
+                                         12 * 568, 13 * 568, 14 * 568, 15 * 568, 0 * 568, 1 * 568, 2 * 568, 3 * 568, 4 * 568, 5 * 568, 6 * 568, 7 * 568,
+                                         8 * 568, 9 * 568, 10 * 568, 11 * 568, 12 * 568, 13 * 568, 14 * 568, 15 * 568};
+static_assert(SP * 4 == 568 && RING == 16, "c_ringoff");
 static __constant__ unsigned c_slide_tbl[8] = {0x0a521452u, 0x1a3b043bu, 0x12e40ce4u, 0x168d088du, 0x15760b76u, 0x051f1b1fu, 0x0dc013c0u, 0x09a917a9u};
 
 // Half-precision pairs of the opt-in fp16 filter stage: IEEE binary16, round to nearest even (HMUL2 / HFMA2: one rounding per
@@ -451,6 +456,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
         const int ty = tile / gx, tx = tile - ty * gx;
         const int x0 = tx * TW, y0 = p.row0 + ty * th;
         const int rl = lt / QW, q = lt - rl * QW;            // this thread's row of a chunk and chain column / pixel column
+        const int rlu = __shfl_sync(0xffffffffu, rl, 0);     // (the same for the whole warp: uniform for the compiler too)
         const unsigned gk = cy.gk;
         // ---- B: column chains of chunk kb, one position per thread (gradients straight from the ring) -> sQ[kb & 1].
         // Unconditional (positions outside the hashed rows produce values nobody reads): straight-line code.
@@ -483,10 +489,11 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
             f32x2 acc[3][3];                                         // [weight-column pair (2mm, 2mm+1)][gx*gx, gx*gy, gy*gy]
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) acc[mm][0] = acc[mm][1] = acc[mm][2] = 0ull;
-            // window row j = ring row (s0 + j) & (RING-1): one of two bases (before / after the ring wraps) plus a compile-time offset
-            const int r0 = s0 & (RING - 1), jw = RING - r0;
-            const float *pA = sRing + r0 * SP + q, *pB = pA - RING * SP;
-            auto wrow = [&](int j) { return (j < jw ? pA : pB) + j * SP; };
+            // window row j = ring row (s0 + j) & (RING-1).  The row of a chunk is the same for a whole warp, so the byte offset of every
+            // window row is a UNIFORM load from a constant table (LDCU, then LDS [R + UR]): one instruction per row
+            const int r0u = (RBP * kb + rlu) & (RING - 1);
+            const char *pq = reinterpret_cast<const char *>(sRing + q);
+            auto wrow = [&](int j) { return reinterpret_cast<const float *>(pq + c_ringoff[r0u + j]); };
             float vprev = wrow(0)[1];
             const float *row = wrow(1);
             float vcur = row[1];
