@@ -32,13 +32,13 @@ constexpr int NCW = NTP / 32 - NPW;          // filter (consumer) warps (3 warpg
 constexpr int NPT = NPW * 32, NCT = NCW * 32;
 constexpr int NBT = NPT / 2;                 // threads of each producer sub-role
 #ifndef RAISR_CHAIN_REGS
-#define RAISR_CHAIN_REGS 48
+#define RAISR_CHAIN_REGS 56
 #endif
 #ifndef RAISR_BUCKET_REGS
 #define RAISR_BUCKET_REGS 56
 #endif
 #ifndef RAISR_CONS_REGS
-#define RAISR_CONS_REGS 96
+#define RAISR_CONS_REGS 88
 #endif
 constexpr int CHAIN_REGS = RAISR_CHAIN_REGS, BUCKET_REGS = RAISR_BUCKET_REGS, CONS_REGS = RAISR_CONS_REGS;   // setmaxnreg targets: 256*48 + 256*56 + 384*96 <= 896*72 registers of the CTA
                                                                    // (measured, round 1: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms; round 2: DESIGN.md section 4)
