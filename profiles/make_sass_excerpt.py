@@ -29,7 +29,7 @@ out = ["SASS of the shipped hot instantiation raisr_frame_pipe_kernel<uint8_t, 4
        % (ops["FFMA2"], ops["FMUL2"], ops["UBLKCP"], ops["UTMALDG"]),
        "  SYNCS %d (mbarrier), USETMAXREG %d (setmaxnreg), BAR %d (named barriers, immediate id and thread count), uniform datapath R2UR/LDCU/U* %d"
        % (ops["SYNCS"], ops["USETMAXREG"], ops["BAR"], sum(v for k, v in ops.items() if k[0] == "U" or k in ("R2UR", "LDCU"))), ""]
-out.append("---- role split: the three warp roles re-balance the register file (setmaxnreg 48 / 56 / 96) --------------------------------")
+out.append("---- role split: the three warp roles re-balance the register file (setmaxnreg 56 / 56 / 88) --------------------------------")
 out += [L[k] for k, l in enumerate(L) if "USETMAXREG" in l] + [""]
 i = find(r"FMUL2")
 out.append("---- stage B (chain warps): structure-tensor column chains, one (row, column) position per thread ----------------------------")

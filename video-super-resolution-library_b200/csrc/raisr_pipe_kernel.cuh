@@ -12,8 +12,8 @@
 // warps hand over a pair of bucket tiles guarded by hardware named barriers (bar.arrive / bar.sync, full and empty per
 // tile buffer: the waiting side blocks without consuming issue slots).
 //
-// Register file: the CTA is launched with 72 registers per thread; the chain warpgroups drop to 48, the bucket warpgroups to
-// 56 and the filter warpgroups rise to 96 (setmaxnreg).  The upscaled rows of chunk k+2 are fetched from global memory before the barrier
+// Register file: the CTA is launched with 72 registers per thread; the chain and the bucket warpgroups drop to 56, the filter
+// warpgroups rise to 88 (setmaxnreg; 48 / 56 / 96 while the filter warps were the bottleneck).  The upscaled rows of chunk k+2 are fetched from global memory before the barrier
 // of chunk k and stored into free ring slots after stage B (latency hidden).
 //
 // Round 2: stage D walks down pixel columns with the patch values in registers (sliding window, rotating chain ownership: see
@@ -40,7 +40,7 @@ constexpr int NBT = NPT / 2;                 // threads of each producer sub-rol
 #ifndef RAISR_CONS_REGS
 #define RAISR_CONS_REGS 88
 #endif
-constexpr int CHAIN_REGS = RAISR_CHAIN_REGS, BUCKET_REGS = RAISR_BUCKET_REGS, CONS_REGS = RAISR_CONS_REGS;   // setmaxnreg targets: 256*48 + 256*56 + 384*96 <= 896*72 registers of the CTA
+constexpr int CHAIN_REGS = RAISR_CHAIN_REGS, BUCKET_REGS = RAISR_BUCKET_REGS, CONS_REGS = RAISR_CONS_REGS;   // setmaxnreg targets: 256*56 + 256*56 + 384*88 <= 896*72 registers of the CTA
                                                                    // (measured, round 1: 48/48/104 0.615 ms, 56/56/88 0.606 ms, 64/64/80 0.615 ms, 48/64/88 0.600 ms; round 2: DESIGN.md section 4)
 static_assert(NBT * (CHAIN_REGS + BUCKET_REGS) + NCT * CONS_REGS <= NTP * 72, "register file of the CTA");
 constexpr int RBP = 2;                       // filtered rows per producer chunk (RBP * QW == NBT positions)
