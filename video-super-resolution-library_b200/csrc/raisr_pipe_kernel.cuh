@@ -19,7 +19,7 @@
 // Round 2: stage D walks down pixel columns with the patch values in registers (sliding window, rotating chain ownership: see
 // pipe_filter_pass); two passes can be chained in one cooperative launch.  The kernel is bound by instruction issue.
 //
-// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite, tools/kbench.py); 0.511 ms vs 0.85 ms per 4K frame.
+// STATUS: bit-identical to raisr_pass_kernel (same GPU parity suite, tools/kbench.py); 0.505 ms vs 0.85 ms per 4K frame.
 #pragma once
 #include "raisr_kernels.cuh"
 #include "raisr_gw_tables.h"
