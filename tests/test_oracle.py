@@ -67,6 +67,22 @@ def test_resize_2x_closed_form():
             assert up[Y, X] == (s + 8) >> 4
 
 
+def test_exported_standin_resize_equals_the_oracle_resize():
+    """oracle/_build/libipp_standin.so (the stand-in's resize on its own, timed by bench.py's cpu_baseline context) is the same
+    arithmetic as the oracle's resize: 2x and 1.5x, odd sizes."""
+    import ctypes as C, os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_build", "libipp_standin.so")
+    if not os.path.exists(path):
+        T.build_oracle()
+    S = C.CDLL(path)
+    rs = np.random.RandomState(5)
+    for (w, h, ow, oh) in ((64, 40, 128, 80), (37, 21, 74, 42), (64, 40, 96, 60), (50, 34, 75, 51)):
+        a = np.ascontiguousarray(rs.randint(0, 256, size=(h, w)).astype(np.uint8))
+        up = np.zeros((oh, ow), np.uint8)
+        assert S.standin_resize_8u(C.c_void_p(a.ctypes.data), w, h, w, C.c_void_p(up.ctypes.data), ow, oh, ow) == 0
+        assert np.array_equal(up, T.oracle_resize(a, ow, oh)), (w, h, ow, oh)
+
+
 def test_hashed_column_range():
     """Column loop of processSegment (Raisr.cpp:1065-1066,1246-1250): c_end = 6 + 8*floor((W-12)/8) for W >= 28."""
     import ctypes as C
