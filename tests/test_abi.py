@@ -172,3 +172,18 @@ def test_sliding_window_schedule_and_tree_table():
     src = open(os.path.join(root, "video-super-resolution-library_b200", "csrc", "raisr_pipe_kernel.cuh")).read()
     tbl = re.search(r"c_slide_tbl\[8\] = \{([^}]*)\}", src).group(1)
     assert [int(x.strip().rstrip("u"), 16) for x in tbl.split(",")] == words
+
+
+def test_host_copy_rows_of_the_pageable_path_equals_memcpy(tmp_path):
+    """csrc/raisr_hostcopy.cpp (streaming-store row copies between the caller's pageable planes and the staging planes): 400 random
+    sizes / alignments / strides against memcpy(), with guard bytes, in whichever mode this CPU selects and in the memcpy mode."""
+    import subprocess
+    src = os.path.join(T.PKG_DIR, "csrc")
+    exe = str(tmp_path / "hostcopy_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + src, os.path.join(T.ROOT, "tests", "harness", "hostcopy_check.cpp"),
+                           os.path.join(src, "raisr_hostcopy.cpp"), "-o", exe])
+    for env in ({}, {"RAISR_CUDA_NT_COPY": "0"}):
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+        if env:
+            assert r.stdout.startswith("mode 0")

@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -30,6 +31,7 @@
 
 #include "raisr_kernels.cuh"
 #include "raisr_launch.h"
+#include "raisr_hostcopy.h"
 #include "raisr_model.h"
 #include "x86_tables.h"
 
@@ -129,31 +131,49 @@ public:
             threads_.emplace_back([this, device, bind] {
                 if (bind) cudaSetDevice(device);
                 for (;;) {
-                    std::function<void()> job;
+                    Job job;
                     {
                         std::unique_lock<std::mutex> lk(m_);
                         cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
                         if (q_.empty()) return;
-                        job = std::move(q_.front());
-                        q_.pop_front();
+                        // the oldest job whose event has completed; if none has, the oldest one (block on its event).  A thread
+                        // never sleeps on a late event (the chroma planes' D2H) while an earlier band is ready to be delivered.
+                        auto pick = q_.begin();
+                        for (auto it = q_.begin(); it != q_.end(); ++it)
+                            if (!it->ev || cudaEventQuery(it->ev) != cudaErrorNotReady) { pick = it; break; }
+                        job = std::move(*pick);
+                        q_.erase(pick);
                     }
-                    job();
+                    if (job.ev) cudaEventSynchronize(job.ev);
+                    job.fn();
                     {
                         std::lock_guard<std::mutex> lk(m_);
-                        if (--pending_ == 0) done_.notify_all();
+                        --pending_;
+                        if (--group_pending_[job.group] == 0) done_.notify_all();
                     }
                 }
             });
     }
-    void submit(std::function<void()> job)
+    // fn runs on a pool thread once ev (may be null) has completed; jobs of one group (0 .. kGroups-1) can be waited for on their own
+    void submit(cudaEvent_t ev, std::function<void()> fn, int group = 0)
     {
-        if (threads_.empty()) { job(); return; }
+        if (threads_.empty()) {
+            if (ev) cudaEventSynchronize(ev);
+            fn();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(m_);
-            q_.push_back(std::move(job));
+            q_.push_back(Job{ev, std::move(fn), group});
             ++pending_;
+            ++group_pending_[group];
         }
         cv_.notify_one();
+    }
+    void wait_group(int group)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this, group] { return group_pending_[group] == 0; });
     }
     void wait_all()
     {
@@ -171,18 +191,25 @@ public:
     }
 
 private:
+    static constexpr int kGroups = 3;
+    struct Job {
+        cudaEvent_t ev = nullptr;
+        std::function<void()> fn;
+        int group = 0;
+    };
+    int group_pending_[kGroups] = {0, 0, 0};
     std::vector<std::thread> threads_;
     std::mutex m_;
     std::condition_variable cv_, done_;
-    std::deque<std::function<void()>> q_;
+    std::deque<Job> q_;
     int pending_ = 0;
     bool stop_ = false;
 };
 
+// (raisr_hostcopy.cpp: streaming stores -- every destination of this path is written once and read by someone else)
 static void copy_rows(void *dst, size_t dstep, const void *src, size_t sstep, size_t row_bytes, int rows)
 {
-    if (dstep == row_bytes && sstep == row_bytes) { memcpy(dst, src, row_bytes * (size_t)rows); return; }
-    for (int y = 0; y < rows; ++y) memcpy(static_cast<char *>(dst) + (size_t)y * dstep, static_cast<const char *>(src) + (size_t)y * sstep, row_bytes);
+    host_copy_rows(dst, dstep, src, sstep, row_bytes, rows);
 }
 
 }  // namespace raisr
@@ -255,6 +282,7 @@ struct raisr_cuda_engine {
     unsigned *h_err = nullptr, *d_err = nullptr;   // page-locked, device-mapped word: an in-kernel flag wait timed out (checked after every frame)
     // RAISR_CUDA_TIMING=1: per-stage device times of the host-pointer call, printed when the engine is destroyed
     bool timing = false; cudaEvent_t tev[3] = {nullptr, nullptr, nullptr}; double t_h2d = 0, t_kern = 0; unsigned long long t_n = 0;
+    double t_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // RAISR_CUDA_TIMING: host-side phase marks of process_host_pipe (sums of microseconds since entry)
     unsigned *d_chroma_ready = nullptr;  // [0] sequence number of the last frame whose chroma planes have arrived (H2D on stream_uv), [1] CTAs done with them (running total)
     unsigned chroma_seq = 0, chroma_done_target = 0;
     unsigned band_target[kMaxBands] = {};  // running totals the D2H stream waits for, per output row band
@@ -962,6 +990,8 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
 {
     const size_t bps = e->bps;
     const bool memops = e->wait_value32 && e->write_value32 && !e->no_memops;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto mark = [&](int i) { if (e->timing && e->t_n >= 8) e->t_host[i] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(); };
 
     // ---- pageable caller planes: go through page-locked staging planes, bytes moved by the copy threads ------------------
     const void *probe = nullptr;
@@ -988,17 +1018,31 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
             const size_t sstep[3] = {in_y_step, in_u_step, in_v_step};
             late_inputs = memops && e->split_h2d && e->in_h >= 256;
             const int early_rows = late_inputs ? std::max(64, (e->in_h / 8 + 15) & ~15) : 0;
+            // luma rows first (group 1: their H2D copy is what the running kernel waits for), then the chroma planes (group 2),
+            // every plane cut so that all copy threads have work
             const int parts = std::max(1, e->copy_threads);
-            for (int i = 0; i < (chroma ? 3 : 1); ++i)
-                for (int k = 0; k < (i == 0 ? parts : 1); ++k) {
-                    const int first = i == 0 ? early_rows : 0, n = i == 0 ? parts : 1;
+            auto stage_rows = [&](int i, int r0, int r1, int group) {
+                if (r1 <= r0) return;
+                void *dst = static_cast<char *>(e->h_stage_in[i]) + (size_t)r0 * irow[i];
+                const void *sp = static_cast<const char *>(src[i]) + (size_t)r0 * sstep[i];
+                const size_t ss = sstep[i], rb = irow[i];
+                if (group < 0) copy_rows(dst, rb, sp, ss, rb, r1 - r0);
+                else e->pool->submit(nullptr, [dst, sp, ss, rb, r0, r1] { copy_rows(dst, rb, sp, ss, rb, r1 - r0); }, group);
+            };
+            // the early rows are on the critical path (nothing runs until they are on the device): all copy threads and this one
+            for (int k = 1; k <= parts && early_rows; ++k)
+                stage_rows(0, (int)((long long)early_rows * k / (parts + 1)), (int)((long long)early_rows * (k + 1) / (parts + 1)), 0);
+            for (int i = 0; i < (chroma ? 3 : 1); ++i) {
+                const int first = i == 0 ? early_rows : 0, n = i == 0 ? parts : std::max(1, parts / 2);
+                for (int k = 0; k < n; ++k) {
                     const int r0 = first + (int)((long long)(irows[i] - first) * k / n), r1 = first + (int)((long long)(irows[i] - first) * (k + 1) / n);
-                    void *dst = static_cast<char *>(e->h_stage_in[i]) + (size_t)r0 * irow[i];
-                    const void *sp = static_cast<const char *>(src[i]) + (size_t)r0 * sstep[i];
-                    const size_t ss = sstep[i], rb = irow[i];
-                    e->pool->submit([dst, sp, ss, rb, r0, r1] { copy_rows(dst, rb, sp, ss, rb, r1 - r0); });
+                    stage_rows(i, r0, r1, i == 0 ? 1 : 2);
                 }
-            if (early_rows) copy_rows(e->h_stage_in[0], irow[0], in_y, in_y_step, irow[0], early_rows);
+            }
+            if (early_rows) {
+                stage_rows(0, 0, early_rows / (parts + 1), -1);
+                e->pool->wait_group(0);
+            }
             if (!late_inputs) e->pool->wait_all();
             in_y = e->h_stage_in[0]; in_y_step = irow[0];
             if (chroma) { in_u = e->h_stage_in[1]; in_v = e->h_stage_in[2]; in_u_step = in_v_step = irow[1]; }
@@ -1013,10 +1057,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         char *dst = static_cast<char *>(user_out[i]) + (size_t)r0 * user_ostep[i];
         const char *src = static_cast<const char *>(e->h_stage_out[i]) + (size_t)r0 * orow[i];
         const size_t ds = user_ostep[i], rb = orow[i];
-        e->pool->submit([dst, src, ds, rb, r0, r1, ev] {
-            if (ev) cudaEventSynchronize(ev);
-            copy_rows(dst, ds, src, rb, rb, r1 - r0);
-        });
+        e->pool->submit(ev, [dst, src, ds, rb, r0, r1] { copy_rows(dst, ds, src, rb, rb, r1 - r0); });
     };
 
     const void *csrc[2] = {in_u, in_v};
@@ -1033,6 +1074,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         in_ready = e->d_in_ready;
     }
     const int rows0 = split_row ? split_row : e->in_h;
+    mark(0);                                                                // early rows staged
     if (e->timing) cudaEventRecord(e->tev[0], e->stream);
     CUDA_OK(cudaMemcpy2DAsync(e->d_in[0].ptr, e->d_in[0].pitch, in_y, in_y_step, e->in_w * bps, rows0, cudaMemcpyHostToDevice, e->stream));
     if (e->timing) cudaEventRecord(e->tev[1], e->stream);
@@ -1050,7 +1092,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         }
     }
     if (split_row) CUDA_OK(cudaEventRecord(e->ev_uv, e->stream));           // part 2 behind part 1 (same copy engine anyway)
-    auto enqueue_rest_of_input = [&]() -> int {
+    auto enqueue_rest_of_luma = [&]() -> int {
         if (split_row) {
             CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
             CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
@@ -1064,6 +1106,9 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         } else if (chroma) {
             CUDA_OK(cudaEventRecord(e->ev_in, e->stream));
         }
+        return 0;
+    };
+    auto enqueue_chroma_in = [&]() -> int {
         if (chroma) {
             if (memops) {
                 CUDA_OK(cudaStreamWaitEvent(e->stream_uv, e->ev_in, 0));
@@ -1080,7 +1125,8 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         return 0;
     };
     if (!late_inputs) {
-        const int rc_in = enqueue_rest_of_input();
+        int rc_in = enqueue_rest_of_luma();
+        if (!rc_in) rc_in = enqueue_chroma_in();
         if (rc_in) return rc_in;
     }
     for (unsigned i = 0; i < e->cfg.passes; ++i)
@@ -1095,9 +1141,14 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
                       tail_direct ? const_cast<void *>(tail_dev) : nullptr, out_y_step, split_row);
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->tev[2], e->stream);
+    mark(1);                                                                // kernel launched
     if (late_inputs) {                                                      // the kernel is running on the early rows: now the rest
-        e->pool->wait_all();
-        const int rc_in = enqueue_rest_of_input();
+        e->pool->wait_group(1);                                             // luma rows staged: their copy and flag first ...
+        int rc_in = enqueue_rest_of_luma();
+        if (rc_in) return rc_in;
+        e->pool->wait_group(2);                                             // ... the chroma planes (needed from the third tile on) behind them
+        mark(2);                                                            // late input rows staged
+        rc_in = enqueue_chroma_in();
         if (rc_in) return rc_in;
     }
 
@@ -1113,12 +1164,19 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         for (int i = 0; i < 2; ++i)
             CUDA_OK(cudaMemcpy2DAsync(cdst[i], cdstep[i], e->d_out[i + 1].ptr, e->d_out[i + 1].pitch, e->out_cw * bps, e->out_ch,
                                       cudaMemcpyDeviceToHost, cs));
-        if (stage_out) {
-            CUDA_OK(cudaEventRecord(e->ev_chroma_out, cs));
-            deliver(1, 0, e->out_ch, e->ev_chroma_out);
-            deliver(2, 0, e->out_ch, e->ev_chroma_out);
-        }
+        if (stage_out) CUDA_OK(cudaEventRecord(e->ev_chroma_out, cs));
     }
+    // (queued BEHIND the luma bands: the pool takes the oldest job whose event has completed and sleeps on the oldest one when none
+    //  has -- which must be the first band, not the chroma planes that the kernel finishes around its middle)
+    auto deliver_chroma = [&]() {
+        if (!(chroma && stage_out)) return;
+        const int parts = std::max(1, e->copy_threads / 2);                     // 2 MB per plane at 4K: not one thread's job
+        for (int i = 1; i <= 2; ++i)
+            for (int k = 0; k < parts; ++k) {
+                const int a = (int)((long long)e->out_ch * k / parts), b = (int)((long long)e->out_ch * (k + 1) / parts);
+                if (b > a) deliver(i, a, b, e->ev_chroma_out);
+            }
+    };
 
     // ---- luma output -------------------------------------------------------------------------------------------------------
     if (band_d2h) {
@@ -1134,7 +1192,12 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
                                       e->out_w * bps, r1 - r0, cudaMemcpyDeviceToHost, e->stream_d2h));
             if (stage_out) {
                 CUDA_OK(cudaEventRecord(e->ev_band[b], e->stream_d2h));
-                deliver(0, r0, r1, e->ev_band[b]);
+                if (b + 2 >= e->n_bands && r1 - r0 >= 2) {                      // the last bands are on the critical path: two threads each
+                    deliver(0, r0, (r0 + r1) / 2, e->ev_band[b]);
+                    deliver(0, (r0 + r1) / 2, r1, e->ev_band[b]);
+                } else {
+                    deliver(0, r0, r1, e->ev_band[b]);
+                }
             }
         }
         if (!tail_direct && e->n_bands > 0 && e->band_row1[e->n_bands - 1] < e->out_h) {
@@ -1144,22 +1207,33 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
                                       static_cast<char *>(e->d_out[0].ptr) + (size_t)r0 * e->d_out[0].pitch, e->d_out[0].pitch,
                                       e->out_w * bps, e->out_h - r0, cudaMemcpyDeviceToHost, e->stream));
         }
+        deliver_chroma();
+        mark(3);                                                            // everything enqueued
         CUDA_OK(cudaStreamSynchronize(e->stream_d2h));
+        mark(4);                                                            // last band copied out
     } else {
+        deliver_chroma();
         CUDA_OK(cudaMemcpy2DAsync(out_y, out_y_step, e->d_out[0].ptr, e->d_out[0].pitch, e->out_w * bps, e->out_h, cudaMemcpyDeviceToHost, e->stream));
     }
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    mark(5);                                                                // kernel done
     if (stage_out) {
         // what the bands did not cover: the rows of the last round of tiles (written in place into the staging plane), or the whole
         // plane when there is no band pipeline
         const int r0 = band_d2h ? (e->n_bands > 0 ? e->band_row1[e->n_bands - 1] : 0) : 0;
-        const int parts = std::max(1, e->copy_threads);
-        for (int k = 0; k < parts && r0 < e->out_h; ++k) {
+        const int parts = e->copy_threads + 1;                              // the copy threads and this one
+        for (int k = 1; k < parts && r0 < e->out_h; ++k) {
             const int a = r0 + (int)((long long)(e->out_h - r0) * k / parts), b = r0 + (int)((long long)(e->out_h - r0) * (k + 1) / parts);
             if (b > a) deliver(0, a, b, nullptr);
         }
+        if (r0 < e->out_h) {
+            const int b = r0 + (int)((long long)(e->out_h - r0) / parts);
+            if (b > r0) copy_rows(static_cast<char *>(user_out[0]) + (size_t)r0 * user_ostep[0], user_ostep[0],
+                                  static_cast<const char *>(e->h_stage_out[0]) + (size_t)r0 * orow[0], orow[0], orow[0], b - r0);
+        }
         e->pool->wait_all();
     }
+    mark(6);                                                                // every staged row delivered
     if (split_row) CUDA_OK(cudaStreamSynchronize(e->stream_h2d));
     if (chroma && memops) CUDA_OK(cudaStreamSynchronize(e->stream_uv));
     if (e->timing) {
@@ -1167,6 +1241,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         cudaEventElapsedTime(&a, e->tev[0], e->tev[1]); cudaEventElapsedTime(&b, e->tev[1], e->tev[2]);
         e->t_h2d += a; e->t_kern += b; e->t_n++;
     }
+    mark(7);
     return RNLErrorNone;
 }
 
@@ -1296,7 +1371,11 @@ void raisr_cuda_destroy(raisr_cuda_engine *e)
     if (!e) return;
     if (e->bind_device) cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    if (e->timing && e->t_n) std::cout << "[RAISR TIMING] frames " << e->t_n << " luma H2D " << 1e3 * e->t_h2d / e->t_n << " us, memset+kernel " << 1e3 * e->t_kern / e->t_n << " us" << std::endl;
+    const double tn = e->t_n > 8 ? double(e->t_n - 8) : 1.0;      // host marks skip the first 8 frames (allocation of the staging planes)
+    if (e->timing && e->t_n) std::cout << "[RAISR TIMING] frames " << e->t_n << " luma H2D " << 1e3 * e->t_h2d / e->t_n << " us, memset+kernel " << 1e3 * e->t_kern / e->t_n << " us; host marks (us since entry): early rows staged " << e->t_host[0] / tn
+                                        << ", launched " << e->t_host[1] / tn << ", late rows staged " << e->t_host[2] / tn << ", all enqueued " << e->t_host[3] / tn
+                                        << ", bands out " << e->t_host[4] / tn << ", kernel done " << e->t_host[5] / tn << ", delivered " << e->t_host[6] / tn
+                                        << ", return " << e->t_host[7] / tn << std::endl;
     for (int i = 0; i < 2; ++i) { cudaFree(e->d_filters[i]); cudaFree(e->d_filters16[i]); cudaFree(e->d_hash[i]); }
     cudaFree(e->d_rows_done);
     for (int i = 0; i < 4; ++i) cudaFree(e->d_lut[i]);
