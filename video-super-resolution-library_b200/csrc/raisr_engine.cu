@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -127,15 +128,24 @@ class CopyPool {
 public:
     void start(int n, int device, bool bind)
     {
+        if (const char *z = std::getenv("RAISR_CUDA_COPY_POLL_US")) poll_us_ = std::max(0, std::min(100000, std::atoi(z)));
         for (int i = 0; i < n; ++i)
             threads_.emplace_back([this, device, bind] {
                 if (bind) cudaSetDevice(device);
                 for (;;) {
                     Job job;
+                    // Inside a frame the next job is at most a band (~30 us) away: poll for that long before sleeping, so that
+                    // neither the submitting thread pays a futex wake-up per job nor the job its latency (the rows delivered
+                    // after the kernel's end and the rows staged ahead of its launch are on the frame's critical path).
+                    for (auto t0 = std::chrono::steady_clock::now(); queued_.load(std::memory_order_acquire) == 0;) {
+                        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(poll_us_)) break;
+                        __builtin_ia32_pause();
+                    }
                     {
                         std::unique_lock<std::mutex> lk(m_);
                         cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
                         if (q_.empty()) return;
+                        queued_.fetch_sub(1, std::memory_order_relaxed);
                         // the oldest job whose event has completed; if none has, the oldest one (block on its event).  A thread
                         // never sleeps on a late event (the chroma planes' D2H) while an earlier band is ready to be delivered.
                         auto pick = q_.begin();
@@ -165,18 +175,22 @@ public:
         {
             std::lock_guard<std::mutex> lk(m_);
             q_.push_back(Job{ev, std::move(fn), group});
+            queued_.fetch_add(1, std::memory_order_release);
             ++pending_;
             ++group_pending_[group];
         }
         cv_.notify_one();
     }
+    // (the waits poll for a moment before sleeping, like the workers: the caller's thread is on the frame's critical path)
     void wait_group(int group)
     {
+        if (poll([this, group] { return group_pending_[group] == 0; })) return;
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this, group] { return group_pending_[group] == 0; });
     }
     void wait_all()
     {
+        if (poll([this] { return pending_ == 0; })) return;
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this] { return pending_ == 0; });
     }
@@ -191,6 +205,17 @@ public:
     }
 
 private:
+    template <typename Pred> bool poll(Pred done)
+    {
+        for (auto t0 = std::chrono::steady_clock::now(); std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(2 * poll_us_);) {
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (done()) return true;
+            }
+            for (int i = 0; i < 32; ++i) __builtin_ia32_pause();
+        }
+        return false;
+    }
     static constexpr int kGroups = 3;
     struct Job {
         cudaEvent_t ev = nullptr;
@@ -198,6 +223,8 @@ private:
         int group = 0;
     };
     int group_pending_[kGroups] = {0, 0, 0};
+    std::atomic<int> queued_{0};                // jobs in q_ (polled without the lock)
+    int poll_us_ = 100;                         // RAISR_CUDA_COPY_POLL_US: how long an idle worker polls before it sleeps (0: sleep at once)
     std::vector<std::thread> threads_;
     std::mutex m_;
     std::condition_variable cv_, done_;
