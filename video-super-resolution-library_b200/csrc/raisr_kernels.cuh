@@ -45,9 +45,9 @@ struct PassParams {
     int nbuckets;            // 216
     int tile_h;              // output rows per CTA tile, <= TH_MAX (even)
     int vec_store;           // output base and pitch allow 4-pixel vector stores
-    const unsigned *in_ready; // optional (pipelined kernel, split H2D): set to in_seq once the lower part of the input plane has landed
+    const unsigned *in_ready; // optional (pipelined kernel, split H2D): watermark of the input copies, (in_seq << 16) | rows that have landed
     unsigned in_seq;         // sequence number of this frame
-    int in_split_row;        // input rows >= in_split_row are valid once *in_ready == in_seq (rows above: stream order)
+    int in_split_row;        // input rows < in_split_row are valid by stream order; row r >= in_split_row once the watermark has passed r
     unsigned *err_flag;      // optional: set to 1 when an in-kernel flag wait times out (a copy the kernel waits for never landed)
     // chained two-pass launch (pipelined kernel): the first pass counts finished tiles per tile row, the second waits for the tile
     // rows of the first that cover the input rows it reads

@@ -59,7 +59,8 @@ constexpr size_t POFF_LUT = (POFF_HASH2 + 2 * (size_t)PHH * OVW + 15) & ~(size_t
 constexpr size_t POFF_RING = POFF_LUT + LUT_WORDS * sizeof(unsigned);
 constexpr size_t POFF_Q = POFF_RING + sizeof(float) * RING * SP;           // 2 chunks of column chains
 constexpr size_t POFF_MBAR = POFF_Q + sizeof(float) * 2 * QCHUNK;          // filter-slice mbarrier
-constexpr size_t PIPE_SMEM_BYTES = POFF_MBAR + 16;
+constexpr size_t POFF_INDONE = POFF_MBAR + 16;                             // split H2D: "the whole input plane has arrived" (chain leader -> filter warps)
+constexpr size_t PIPE_SMEM_BYTES = POFF_INDONE + 16;
 static_assert(PIPE_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(((PTH_MAX + 14) / 2 + 1) * LRP <= PHH * HP, "low-res staging fits in the HR tile");
 // TMA landing zone of stage A's low-res window (raw samples): 128-byte aligned, in the HR tile behind the float staging above
@@ -70,6 +71,13 @@ static_assert(POFF_TMA + 80 * 2 * TMAP_BOX_H <= POFF_HR + sizeof(float) * PHH * 
 // compute-sanitizer's synccheck see that these are partial barriers and not a __syncthreads() some threads skip)
 template <int ID, int COUNT> __device__ __forceinline__ void group_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 #define group_sync(id, count) group_sync_c<(id), (count)>()
+// barrier + OR of a predicate over the group (bar.red): every thread gets the same answer
+template <int ID, int COUNT> __device__ __forceinline__ bool group_or(bool v)
+{
+    unsigned r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 p, %1, 0;\n bar.red.or.pred q, %2, %3, p;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(r) : "r"((unsigned)v), "n"(ID), "n"(COUNT) : "memory");
+    return r != 0u;
+}
 // barrier pair selected by the bucket-tile buffer (0 / 1)
 template <int ID, int COUNT> __device__ __forceinline__ void group_sync_buf(int buf) { if (buf) group_sync_c<ID + 1, COUNT>(); else group_sync_c<ID, COUNT>(); }
 // producer/consumer hand-off through hardware named barriers: the waiting side blocks in bar.sync (no issue slots, unlike an
@@ -202,6 +210,29 @@ __device__ __forceinline__ void spin_wait_flag(const unsigned *flag, unsigned se
     }
 }
 
+// same, for the input watermark (frame sequence number << 16 | rows that have arrived): wait until *flag has reached `need`, in
+// wrap-around arithmetic (the sequence number wraps every 65536 frames).  Returns the value seen (need itself after a timeout).
+__device__ __forceinline__ unsigned spin_wait_flag_reach(const unsigned *flag, unsigned need, unsigned *err)
+{
+    unsigned long long t0 = 0;
+    for (unsigned n = 1;; ++n) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - need) >= 0) return v;
+        if ((n & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            volatile unsigned *verr = err;
+            const bool failed = verr && *verr != 0;
+            if (failed || t - t0 > 2000000000ull) {
+                if (verr) { *verr = 1u; __threadfence_system(); }
+                return need | 0xffffu;                                        // "everything": no second 2 s wait in a frame that has failed
+            }
+        }
+    }
+}
+
 // same, for a counter that only grows during the launch: wait until *flag >= need
 __device__ __forceinline__ void spin_wait_flag_geq(const unsigned *flag, unsigned need, unsigned *err)
 {
@@ -243,9 +274,13 @@ static __device__ __forceinline__ void producer_chunk_barrier() { group_sync_c<B
 #endif
 
 template <int BAR, int COUNT>
-static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, unsigned *err, bool leader)
+static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, int rows_needed, int rows_total, unsigned *err, bool leader,
+                                                     volatile unsigned *s_all)
 {
-    if (leader) spin_wait_flag(flag, seq, err);
+    if (leader) {
+        const unsigned v = spin_wait_flag_reach(flag, (seq << 16) | (unsigned)rows_needed, err);
+        if ((int)(v - ((seq << 16) | (unsigned)rows_total)) >= 0) *s_all = 1u;   // seen by the filter warps behind this tile's FULL barrier
+    }
     group_sync_c<BAR, COUNT>();
 }
 
@@ -447,7 +482,7 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
     // The two producer roles run as one pipeline over all chunks of all tiles of this CTA: the chain warps are one chunk
     // ahead of the bucket warps (double-buffered chains, buffer = running chunk number & 1, one BAR_PROD per chunk), also
     // across tile (and pass) boundaries, where the chain warps refill the ring while the bucket warps finish the previous tile.
-    bool input_complete = false;
+    int in_known = p.in_split_row;                                       // split H2D: input rows [0, in_known) are known to have arrived
     int dep_known = 0;                                                   // DEP: tile rows [0, dep_known) of the previous pass seen complete
     for (int tile = tile0; tile < ntiles; tile += gridDim.x, ++cy.iter) {
         const int buf = cy.iter & 1;
@@ -572,12 +607,13 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
         if (chain_warp) {
             // split H2D: the lower part of the input plane may still be on its way (own stream, flagged).  Both reader groups
             // look for themselves (the filter warps' stage A): neither is ordered behind the other's wait.
-            if (!DEP && p.in_ready && !input_complete) {
+            if (!DEP && p.in_ready && in_known < p.in_h) {
                 int in_lo, in_last;
                 tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
-                if (in_last >= p.in_split_row) {
-                    wait_split_input<BAR_CHAIN, NBT>(p.in_ready, p.in_seq, p.err_flag, lt == 0);
-                    input_complete = true;
+                if (in_last >= in_known) {                                   // the copies land in row order: wait for the watermark to pass this tile's last row
+                    in_known = min(in_last + 1, p.in_h);
+                    wait_split_input<BAR_CHAIN, NBT>(p.in_ready, p.in_seq, in_known, p.in_h, p.err_flag, lt == 0,
+                                                     reinterpret_cast<volatile unsigned *>(smem_raw + POFF_INDONE));
                 }
             }
             if (DEP) {                                                   // chained pass: the previous pass's rows this tile reads
@@ -749,7 +785,10 @@ __device__ __forceinline__ void pipe_filter_pass(const PassParams &p, unsigned c
             tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
             if (in_last >= p.in_split_row) {
                 group_sync_buf<BAR_FULL, NBT + NCT>(buf);
-                full_taken = input_complete = true;
+                full_taken = true;
+                // "the chain leader has seen the whole plane": the word is written asynchronously to this group, so the threads may
+                // read different values -- the decision must be uniform (it moves a barrier), hence the OR over the group
+                input_complete = group_or<BAR_CONS, NCT>(*reinterpret_cast<volatile unsigned *>(smem_raw + POFF_INDONE) != 0u);
             }
         }
 
@@ -1134,6 +1173,7 @@ __global__ void __launch_bounds__(NTP, 1) raisr_frame_pipe_kernel(const __grid_c
     for (int i = tid0; i < 2 * PHH * (HP - HW); i += NTP)                 // pad columns of both bucket tiles: "not hashed"
         smem_raw[POFF_HASH + (size_t)(i / (HP - HW)) * HP + HW + i % (HP - HW)] = 255;
     if (tid0 == 0) {
+        *reinterpret_cast<volatile unsigned *>(smem_raw + POFF_INDONE) = 0u;
         mbar_init(mslice, 1);
         mbar_init(mslice + 1, 1);                                           // tensor-map loads of stage A
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
