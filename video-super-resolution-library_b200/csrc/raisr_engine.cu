@@ -301,6 +301,7 @@ struct raisr_cuda_engine {
     unsigned *d_in_ready = nullptr;      // watermark of the split H2D: (frame_seq << 16) | input rows that have arrived
     unsigned frame_seq = 0;
     static constexpr int kMaxInChunks = 6;
+    bool in_chunks_ahead = true;     // all of those copies enqueued ahead of the launch (RAISR_CUDA_IN_CHUNKS_AHEAD=0: only the first, the others behind it)
     int in_chunks = 1;               // copies the rows behind the first ones arrive in (watermark after each); RAISR_CUDA_IN_CHUNKS
     // pageable caller planes: page-locked staging planes + copy threads (RAISR_CUDA_STAGE_PAGEABLE=0 / RAISR_CUDA_COPY_THREADS=n)
     bool stage_pageable = true;
@@ -714,6 +715,7 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *c = std::getenv("RAISR_CUDA_TEST_DROP_IN_FLAG")) e->test_drop_in_flag = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_TMA")) e->use_tma = std::atoi(c) != 0;
+    if (const char *c = std::getenv("RAISR_CUDA_IN_CHUNKS_AHEAD")) e->in_chunks_ahead = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_IN_CHUNKS")) e->in_chunks = std::max(1, std::min((int)raisr_cuda_engine::kMaxInChunks, std::atoi(c)));
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));
     {
@@ -1180,9 +1182,11 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     // Ahead of the launch: the first of the copies the kernel will wait for (all of them without a split) -- unless the staging
     // copies of a pageable plane are still running (late_inputs).  Everything else is enqueued right behind the launch: the kernel
     // does not need it for its first ~50 us, and the launch is what the frame's latency hangs on.
+    const bool all_ahead = !late_inputs && (n_chunks <= 1 || e->in_chunks_ahead);
     if (!late_inputs) {
-        int rc_in = n_chunks ? enqueue_luma_chunk(0) : 0;
-        if (!rc_in && n_chunks <= 1) { rc_in = record_luma_in(); if (!rc_in) rc_in = enqueue_chroma_in(); }
+        int rc_in = 0;
+        for (int k = 0; k < (all_ahead ? n_chunks : 1) && k < n_chunks && !rc_in; ++k) rc_in = enqueue_luma_chunk(k);
+        if (!rc_in && all_ahead) { rc_in = record_luma_in(); if (!rc_in) rc_in = enqueue_chroma_in(); }
         if (rc_in) return rc_in;
     }
     for (unsigned i = 0; i < e->cfg.passes; ++i)
@@ -1198,7 +1202,7 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->tev[2], e->stream);
     mark(1);                                                                // kernel launched
-    if (late_inputs || n_chunks > 1) {                                      // the kernel is running on the early rows: now the rest
+    if (late_inputs || !all_ahead) {                                        // the kernel is running on the early rows: now the rest
         for (int k = late_inputs ? 0 : 1; k < n_chunks; ++k) {
             if (late_inputs) e->pool->wait_group(1 + k);                    // this chunk's rows are staged
             const int rc_in = enqueue_luma_chunk(k);
