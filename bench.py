@@ -524,10 +524,10 @@ def main():
     e2e_pageable = None
     try:
         hp = HandlerSession(wl, pinned=False)
-        for _ in range(4):
-            hp.frame()
+        for _ in range(max(4, len(hp.sets))):          # every rotating plane set once: a frame pool recycles its buffers, first-touch
+            hp.frame()                                   # page faults of freshly malloc'ed output planes are not the steady state
         barrier()
-        npg = 2 * FRAMES_PER_STEP
+        npg = 4 * FRAMES_PER_STEP
         t0 = time.perf_counter()
         for _ in range(npg):
             hp.frame()
