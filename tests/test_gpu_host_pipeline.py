@@ -84,8 +84,7 @@ def test_pinned_and_pageable_planes_give_the_same_frame(cfg, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"RAISR_CUDA_SPLIT_H2D": "0"}, {"RAISR_CUDA_TAIL_IN_PLACE": "0"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"},
-                                 {"RAISR_CUDA_KERNEL": "tile"}, {"RAISR_CUDA_NO_MEMOPS": "1"}, {"RAISR_CUDA_IN_CHUNKS": "4"},
-                                 {"RAISR_CUDA_IN_CHUNKS": "6", "RAISR_CUDA_IN_CHUNKS_AHEAD": "0"}],
+                                 {"RAISR_CUDA_KERNEL": "tile"}, {"RAISR_CUDA_NO_MEMOPS": "1"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_copy_strategies_are_invisible(env, monkeypatch):
     cfg = CONFIGS[1]
@@ -172,15 +171,12 @@ def test_two_live_engines_with_different_bit_depths_interleaved():
     e10.close()
 
 
-@pytest.mark.parametrize("chunks", ["1", "4"], ids=lambda c: "copies=" + c)
 @pytest.mark.parametrize("size", [(96, 256), (128, 300), (640, 512), (1000, 600)], ids=lambda s: "%dx%d" % s)
-def test_split_h2d_on_small_tall_frames_with_pinned_planes(size, chunks, monkeypatch):
+def test_split_h2d_on_small_tall_frames_with_pinned_planes(size):
     """in_h >= 256 with fewer tiles than SMs: every tile is a CTA's first, so the filter warps read input rows behind the split
     at kernel start -- they must be ordered behind the watermark the H2D stream writes (page-locked planes make the copy truly
-    async).  copies=4: the rows behind the first ones arrive in four flagged copies, three of them enqueued behind the launch."""
+    async).  1000x600: several rounds of tiles, the chain warps wait once per tile row until the watermark has passed the plane."""
     w, h = size
-    monkeypatch.setenv("RAISR_CUDA_IN_CHUNKS", chunks)
-    monkeypatch.setenv("RAISR_CUDA_IN_CHUNKS_AHEAD", "0")
     f = T.filter_folder("filters_2x/filters_lowres")
     img = T.synth_frame(w, h, 8, seed=w + h, kind="noise")
     ref = T.oracle_process_y(img, 2 * w, 2 * h, T.OracleModel(f, 8))
@@ -216,8 +212,7 @@ def test_setres_rejects_cb_geometry_that_differs_from_cr():
 
 
 @pytest.mark.parametrize("env", [{}, {"RAISR_CUDA_STAGE_PAGEABLE": "0"}, {"RAISR_CUDA_COPY_THREADS": "0"}, {"RAISR_CUDA_COPY_THREADS": "1"},
-                                 {"RAISR_CUDA_NO_MEMOPS": "1"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}, {"RAISR_CUDA_IN_CHUNKS": "4"},
-                                 {"RAISR_CUDA_NT_COPY": "0"}],
+                                 {"RAISR_CUDA_NO_MEMOPS": "1"}, {"RAISR_CUDA_NO_BAND_PIPELINE": "1"}, {"RAISR_CUDA_NT_COPY": "0"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()) or "default")
 def test_pageable_planes_with_padded_steps_through_the_staging_pipeline(env, monkeypatch):
     """Pageable caller planes (what av_frame_get_buffer hands a software filter) travel through the engine's page-locked staging

@@ -216,7 +216,7 @@ private:
         }
         return false;
     }
-    static constexpr int kGroups = 8;
+    static constexpr int kGroups = 3;
     struct Job {
         cudaEvent_t ev = nullptr;
         std::function<void()> fn;
@@ -300,9 +300,6 @@ struct raisr_cuda_engine {
     int tmap_next = 0;
     unsigned *d_in_ready = nullptr;      // watermark of the split H2D: (frame_seq << 16) | input rows that have arrived
     unsigned frame_seq = 0;
-    static constexpr int kMaxInChunks = 6;
-    bool in_chunks_ahead = true;     // all of those copies enqueued ahead of the launch (RAISR_CUDA_IN_CHUNKS_AHEAD=0: only the first, the others behind it)
-    int in_chunks = 1;               // copies the rows behind the first ones arrive in (watermark after each); RAISR_CUDA_IN_CHUNKS
     // pageable caller planes: page-locked staging planes + copy threads (RAISR_CUDA_STAGE_PAGEABLE=0 / RAISR_CUDA_COPY_THREADS=n)
     bool stage_pageable = true;
     int copy_threads = 4;
@@ -715,8 +712,6 @@ int raisr_cuda_create(const raisr_cuda_config *cfg, raisr_cuda_engine **out)
     if (const char *c = std::getenv("RAISR_CUDA_TEST_DROP_IN_FLAG")) e->test_drop_in_flag = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_STAGE_PAGEABLE")) e->stage_pageable = std::atoi(c) != 0;
     if (const char *c = std::getenv("RAISR_CUDA_TMA")) e->use_tma = std::atoi(c) != 0;
-    if (const char *c = std::getenv("RAISR_CUDA_IN_CHUNKS_AHEAD")) e->in_chunks_ahead = std::atoi(c) != 0;
-    if (const char *c = std::getenv("RAISR_CUDA_IN_CHUNKS")) e->in_chunks = std::max(1, std::min((int)raisr_cuda_engine::kMaxInChunks, std::atoi(c)));
     if (const char *c = std::getenv("RAISR_CUDA_COPY_THREADS")) e->copy_threads = std::max(0, std::min(16, std::atoi(c)));
     {
         int coop = 0;
@@ -1064,23 +1059,10 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
             // the early rows are on the critical path (nothing runs until they are on the device): all copy threads and this one
             for (int k = 1; k <= parts && early_rows; ++k)
                 stage_rows(0, (int)((long long)early_rows * k / (parts + 1)), (int)((long long)early_rows * (k + 1) / (parts + 1)), 0);
-            if (late_inputs) {
-                // the same chunks as the H2D copies below (group 1 + chunk), every chunk cut over all copy threads
-                const int nck = std::max(1, std::min(e->in_chunks, (e->in_h - early_rows + 63) / 64));
-                for (int c = 0; c < nck; ++c) {
-                    const int c1 = nck == 1 ? e->in_h : std::min(e->in_h, 2 * early_rows);
-                    const int a = c == 0 ? early_rows : c1 + (int)((long long)(e->in_h - c1) * (c - 1) / (nck - 1));
-                    const int b = c == 0 ? c1 : c1 + (int)((long long)(e->in_h - c1) * c / (nck - 1));
-                    for (int k = 0; k < parts; ++k)
-                        stage_rows(0, a + (int)((long long)(b - a) * k / parts), a + (int)((long long)(b - a) * (k + 1) / parts), 1 + c);
-                }
-                for (int i = 1; i < (chroma ? 3 : 1); ++i) {
-                    const int n = std::max(1, parts / 2);
-                    for (int k = 0; k < n; ++k) stage_rows(i, (int)((long long)irows[i] * k / n), (int)((long long)irows[i] * (k + 1) / n), 1 + nck);
-                }
-            } else {
-                for (int i = 0; i < (chroma ? 3 : 1); ++i)
-                    for (int k = 0; k < parts; ++k) stage_rows(i, (int)((long long)irows[i] * k / parts), (int)((long long)irows[i] * (k + 1) / parts), 1);
+            for (int i = 0; i < (chroma ? 3 : 1); ++i) {
+                const int first = i == 0 ? early_rows : 0, n = i == 0 ? parts : std::max(1, parts / 2);
+                for (int k = 0; k < n; ++k)
+                    stage_rows(i, first + (int)((long long)(irows[i] - first) * k / n), first + (int)((long long)(irows[i] - first) * (k + 1) / n), i == 0 ? 1 : 2);
             }
             if (early_rows) {
                 stage_rows(0, 0, early_rows / (parts + 1), -1);
@@ -1111,19 +1093,10 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     // ---- luma input: rows [0, split_row) ahead of the launch, the rest under the kernel ----------------------------------
     int split_row = 0;
     const unsigned *in_ready = nullptr;
-    int chunk_row[raisr_cuda_engine::kMaxInChunks + 1] = {0};              // rows [chunk_row[k], chunk_row[k+1]): copy k behind the first one
-    int n_chunks = 0;
     if (memops && e->split_h2d && e->in_h >= 256 && e->in_h < 65536) {
         split_row = std::max(64, (e->in_h / 8 + 15) & ~15);
         ++e->frame_seq;
         in_ready = e->d_in_ready;
-        // The rest of the plane goes in a few copies, each followed by a watermark write ((frame << 16) | rows that have landed):
-        // the kernel walks down the plane behind the copy engine instead of waiting for the last row.  The first of them is as
-        // small as the rows copied ahead of the launch, so that on a slow link the kernel's second round of tiles is not held up.
-        n_chunks = std::max(1, std::min(e->in_chunks, (e->in_h - split_row + 63) / 64));
-        chunk_row[0] = split_row;
-        chunk_row[1] = n_chunks == 1 ? e->in_h : std::min(e->in_h, 2 * split_row);
-        for (int k = 2; k <= n_chunks; ++k) chunk_row[k] = chunk_row[1] + (int)((long long)(e->in_h - chunk_row[1]) * (k - 1) / (n_chunks - 1));
     }
     const int rows0 = split_row ? split_row : e->in_h;
     mark(0);                                                                // early rows staged
@@ -1148,14 +1121,16 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     //  the kernel; exercises the bounded spin, the error word and the fall-back to plain stream order)
     const bool drop_flags = e->test_drop_in_flag;
     e->test_drop_in_flag = false;
-    auto enqueue_luma_chunk = [&](int k) -> int {                           // k = 0 .. n_chunks - 1
-        if (k == 0) CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
-        const int r0 = chunk_row[k], r1 = chunk_row[k + 1];
-        if (r1 > r0)
-            CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)r0 * e->d_in[0].pitch, e->d_in[0].pitch,
-                                      static_cast<const char *>(in_y) + (size_t)r0 * in_y_step, in_y_step, e->in_w * bps, r1 - r0,
-                                      cudaMemcpyHostToDevice, e->stream_h2d));
-        if (!drop_flags && e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, (e->frame_seq << 16) | (unsigned)r1, 0) != 0)
+    // The rest of the plane in ONE copy followed by the watermark write ((frame << 16) | rows that have landed).  (The kernel's
+    // protocol allows several flagged copies; measured, they only cost: 4 copies 1670 vs 1765 frames/s at N = 1, 7689 vs 7778 on
+    // 8 GPUs whose host link is slower than the kernel, 1545 vs 1580 with pageable planes -- DESIGN.md section 5.)
+    auto enqueue_rest_of_luma = [&]() -> int {
+        if (!split_row) return 0;
+        CUDA_OK(cudaStreamWaitEvent(e->stream_h2d, e->ev_uv, 0));
+        CUDA_OK(cudaMemcpy2DAsync(static_cast<char *>(e->d_in[0].ptr) + (size_t)split_row * e->d_in[0].pitch, e->d_in[0].pitch,
+                                  static_cast<const char *>(in_y) + (size_t)split_row * in_y_step, in_y_step, e->in_w * bps, e->in_h - split_row,
+                                  cudaMemcpyHostToDevice, e->stream_h2d));
+        if (!drop_flags && e->write_value32(e->stream_h2d, (unsigned long long)(uintptr_t)e->d_in_ready, (e->frame_seq << 16) | (unsigned)e->in_h, 0) != 0)
             return memop_failed("cuStreamWriteValue32");
         return 0;
     };
@@ -1179,14 +1154,12 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
         }
         return 0;
     };
-    // Ahead of the launch: the first of the copies the kernel will wait for (all of them without a split) -- unless the staging
-    // copies of a pageable plane are still running (late_inputs).  Everything else is enqueued right behind the launch: the kernel
-    // does not need it for its first ~50 us, and the launch is what the frame's latency hangs on.
-    const bool all_ahead = !late_inputs && (n_chunks <= 1 || e->in_chunks_ahead);
+    // Every copy the kernel waits for is enqueued ahead of the launch -- unless the staging copies of a pageable plane are still
+    // running (late_inputs): then right behind it.
     if (!late_inputs) {
-        int rc_in = 0;
-        for (int k = 0; k < (all_ahead ? n_chunks : 1) && k < n_chunks && !rc_in; ++k) rc_in = enqueue_luma_chunk(k);
-        if (!rc_in && all_ahead) { rc_in = record_luma_in(); if (!rc_in) rc_in = enqueue_chroma_in(); }
+        int rc_in = enqueue_rest_of_luma();
+        if (!rc_in) rc_in = record_luma_in();
+        if (!rc_in) rc_in = enqueue_chroma_in();
         if (rc_in) return rc_in;
     }
     for (unsigned i = 0; i < e->cfg.passes; ++i)
@@ -1202,15 +1175,12 @@ int process_host_pipe(raisr_cuda_engine *e, const void *in_y, size_t in_y_step, 
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->tev[2], e->stream);
     mark(1);                                                                // kernel launched
-    if (late_inputs || !all_ahead) {                                        // the kernel is running on the early rows: now the rest
-        for (int k = late_inputs ? 0 : 1; k < n_chunks; ++k) {
-            if (late_inputs) e->pool->wait_group(1 + k);                    // this chunk's rows are staged
-            const int rc_in = enqueue_luma_chunk(k);
-            if (rc_in) return rc_in;
-        }
-        int rc_in = record_luma_in();
+    if (late_inputs) {                                                      // the kernel is running on the early rows: now the rest
+        e->pool->wait_group(1);                                             // luma rows staged: their copy and watermark first ...
+        int rc_in = enqueue_rest_of_luma();
+        if (!rc_in) rc_in = record_luma_in();
         if (rc_in) return rc_in;
-        if (late_inputs) e->pool->wait_group(1 + n_chunks);                 // the chroma planes (needed from the third tile on) behind the luma rows
+        e->pool->wait_group(2);                                             // ... the chroma planes (needed from the third tile on) behind them
         mark(2);                                                            // late input rows staged
         rc_in = enqueue_chroma_in();
         if (rc_in) return rc_in;
