@@ -211,7 +211,7 @@ __device__ __forceinline__ void spin_wait_flag(const unsigned *flag, unsigned se
 }
 
 // same, for the input watermark (frame sequence number << 16 | rows that have arrived): wait until *flag has reached `need`, in
-// wrap-around arithmetic (the sequence number wraps every 65536 frames).  Returns the value seen (need itself after a timeout).
+// wrap-around arithmetic (the sequence number wraps every 65536 frames).  Returns the value seen ("every row" after a timeout).
 __device__ __forceinline__ unsigned spin_wait_flag_reach(const unsigned *flag, unsigned need, unsigned *err)
 {
     unsigned long long t0 = 0;
@@ -274,14 +274,16 @@ static __device__ __forceinline__ void producer_chunk_barrier() { group_sync_c<B
 #endif
 
 template <int BAR, int COUNT>
-static __device__ __noinline__ void wait_split_input(const unsigned *flag, unsigned seq, int rows_needed, int rows_total, unsigned *err, bool leader,
+static __device__ __noinline__ bool wait_split_input(const unsigned *flag, unsigned seq, int rows_needed, int rows_total, unsigned *err, bool leader,
                                                      volatile unsigned *s_all)
 {
+    bool all = false;
     if (leader) {
         const unsigned v = spin_wait_flag_reach(flag, (seq << 16) | (unsigned)rows_needed, err);
-        if ((int)(v - ((seq << 16) | (unsigned)rows_total)) >= 0) *s_all = 1u;   // seen by the filter warps behind this tile's FULL barrier
+        all = (int)(v - ((seq << 16) | (unsigned)rows_total)) >= 0;
+        if (all) *s_all = 1u;                                                // seen by the filter warps behind this tile's FULL barrier
     }
-    group_sync_c<BAR, COUNT>();
+    return group_or<BAR, COUNT>(all);                                        // the group's barrier; true: the whole plane has arrived, no further waits
 }
 
 // Chroma planes: plain cheap upscale (Raisr.cpp:1373-1388) of this CTA's share of the planes, slice sl of nslices, by the filter
@@ -612,8 +614,9 @@ __device__ __forceinline__ void pipe_producer_pass(const PassParams &p, unsigned
                 tile_input_rows<UPS>(p, y0, th, in_lo, in_last);
                 if (in_last >= in_known) {                                   // the copies land in row order: wait for the watermark to pass this tile's last row
                     in_known = min(in_last + 1, p.in_h);
-                    wait_split_input<BAR_CHAIN, NBT>(p.in_ready, p.in_seq, in_known, p.in_h, p.err_flag, lt == 0,
-                                                     reinterpret_cast<volatile unsigned *>(smem_raw + POFF_INDONE));
+                    if (wait_split_input<BAR_CHAIN, NBT>(p.in_ready, p.in_seq, in_known, p.in_h, p.err_flag, lt == 0,
+                                                         reinterpret_cast<volatile unsigned *>(smem_raw + POFF_INDONE)))
+                        in_known = p.in_h;
                 }
             }
             if (DEP) {                                                   // chained pass: the previous pass's rows this tile reads
